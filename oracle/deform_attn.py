@@ -1,0 +1,130 @@
+"""Oracle for the DAT-style deformable attention of the TSA / SCA layers.
+
+Functional CPU restatement (parameters passed as a ``state_dict``-keyed dict)
+of ``TSADeformableAttention.forward`` (TSA_deform_attn.py:128-337) and
+``SCADeformableAttention.forward`` (SCA_deform_attn.py:180-421, n_views == 1;
+the reference itself fails for more views).  It materialises the
+dense (Nq, Ns) attention matrix exactly like the reference, so it is only
+usable at small BEV sizes; ``rpe_attention_rows`` evaluates a block of query
+rows for larger shapes (row chunking is exact: every row is independent).
+
+Pinned by ``tests/golden/tsa_*.npz`` / ``sca_*.npz`` (outputs and gradients
+of the real reference modules, made by ``tests/golden/make_golden.py``).
+"""
+import torch
+import torch.nn.functional as F
+
+
+def normalized_grid(H, W, dtype=torch.float32, device="cpu"):
+    """(H, W, 2) in (y, x): arange -> /(size-1) -> *2 -> -1   (TSA_deform_attn.py:98-109)."""
+    ys = torch.arange(0, H, dtype=dtype, device=device).div(H - 1.0).mul(2.0).sub(1.0)
+    xs = torch.arange(0, W, dtype=dtype, device=device).div(W - 1.0).mul(2.0).sub(1.0)
+    gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+    return torch.stack((gy, gx), -1)
+
+
+def offset_network(p, prefix, x, kernel_size, stride):
+    """depthwise conv -> LayerNorm over channels -> GELU -> 1x1 (no bias).
+    TSA_deform_attn.py:54-68, SCA_deform_attn.py:56-77, model_utils.py:51-59."""
+    w0 = p[prefix + ".0.weight"]
+    pad = kernel_size // 2 if kernel_size != stride else 0
+    y = F.conv2d(x, w0, p[prefix + ".0.bias"], stride=stride, padding=pad, groups=x.shape[1])
+    y = y.permute(0, 2, 3, 1)
+    y = F.layer_norm(y, (y.shape[-1],), p[prefix + ".1.norm.weight"], p[prefix + ".1.norm.bias"])
+    y = F.gelu(y.permute(0, 3, 1, 2))
+    return F.conv2d(y, p[prefix + ".3.weight"])
+
+
+def rpe_bias_dense(rpe_table, pos, Hq, Wq, n_groups):
+    """Sampled relative-position bias, (B*h, Nq, Ns).
+    pos (B*g, Ns, 2) in (y, x).  TSA_deform_attn.py:264-305, SCA_deform_attn.py:360-394."""
+    Bg, Ns, _ = pos.shape
+    h = rpe_table.shape[0]
+    n = h // n_groups
+    qg = normalized_grid(Hq, Wq, pos.dtype, pos.device).reshape(1, Hq * Wq, 1, 2)
+    disp = (qg - pos[:, None]).mul(0.5)                            # (B*g, Nq, Ns, 2) (y,x)
+    table = rpe_table.reshape(1, n_groups, n, *rpe_table.shape[1:]).expand(Bg // n_groups, -1, -1, -1, -1)
+    table = table.reshape(Bg, n, *rpe_table.shape[1:])
+    bias = F.grid_sample(table, disp.flip(-1), mode="bilinear", align_corners=True)
+    return bias.reshape(Bg * n, Hq * Wq, Ns)
+
+
+def rpe_attention_dense(q, k, v, rpe_table, pos, Hq, Wq, n_groups, scale):
+    """softmax_j(q.k*scale + bias) . v ; q (B*h,Dh,Nq), k/v (B*h,Dh,Ns) -> (B*h,Dh,Nq).
+    TSA_deform_attn.py:245-330, SCA_deform_attn.py:331-411."""
+    attn = torch.einsum("bcm,bcn->bmn", q, k).mul(scale)
+    attn = attn + rpe_bias_dense(rpe_table, pos, Hq, Wq, n_groups)
+    attn = F.softmax(attn, dim=2)
+    return torch.einsum("bmn,bcn->bcm", attn, v)
+
+
+def rpe_attention_rows(q, k, v, rpe_table, pos, Hq, Wq, n_groups, scale, row0, row1):
+    """Same as rpe_attention_dense but only for query indices [row0,row1)."""
+    Bg, Ns, _ = pos.shape
+    h = rpe_table.shape[0]
+    n = h // n_groups
+    qg = normalized_grid(Hq, Wq, pos.dtype, pos.device).reshape(1, Hq * Wq, 1, 2)[:, row0:row1]
+    disp = (qg - pos[:, None]).mul(0.5)
+    table = rpe_table.reshape(1, n_groups, n, *rpe_table.shape[1:]).expand(Bg // n_groups, -1, -1, -1, -1)
+    table = table.reshape(Bg, n, *rpe_table.shape[1:])
+    bias = F.grid_sample(table, disp.flip(-1), mode="bilinear", align_corners=True)
+    bias = bias.reshape(Bg * n, row1 - row0, Ns)
+    attn = torch.einsum("bcm,bcn->bmn", q[:, :, row0:row1], k).mul(scale) + bias
+    return torch.einsum("bmn,bcn->bcm", F.softmax(attn, dim=2), v)
+
+
+def _attend(p, x_sampled, query, pos, n_heads, n_groups, Hq, Wq):
+    B, C = query.shape[:2]
+    Dh = C // n_heads
+    Ns = x_sampled.shape[-1]
+    q = query.reshape(B * n_heads, Dh, Hq * Wq)                     # proj_q is never applied
+    k = F.conv2d(x_sampled, p["proj_k.weight"], p["proj_k.bias"]).reshape(B * n_heads, Dh, Ns)
+    v = F.conv2d(x_sampled, p["proj_v.weight"], p["proj_v.bias"]).reshape(B * n_heads, Dh, Ns)
+    out = rpe_attention_dense(q, k, v, p["rpe_table"], pos, Hq, Wq, n_groups, Dh ** -0.5)
+    return out.reshape(B, C, Hq, Wq)
+
+
+def tsa_forward(p, x, query, n_heads, n_groups, kernel_size, stride, scale_offset_range=True):
+    """TSADeformableAttention.forward; returns (out, pos) with pos (B*g,Hk,Wk,2) in (y,x)."""
+    if x is None:
+        x = query.clone()
+    B, C, H, W = x.shape
+    Cg = C // n_groups
+    off = offset_network(p, "conv_offset", query.reshape(B * n_groups, Cg, H, W), kernel_size, stride)
+    Hk, Wk = off.shape[-2:]
+    if scale_offset_range:
+        rng = torch.tensor([1.0 / (Hk - 1.0), 1.0 / (Wk - 1.0)]).reshape(1, 2, 1, 1)
+        off = off.tanh().mul(rng).mul(0.5)
+    pos = off.permute(0, 2, 3, 1) + normalized_grid(Hk, Wk)[None]
+    if not scale_offset_range:
+        pos = pos.clamp(-1.0, 1.0)
+    xs = F.grid_sample(x.reshape(B * n_groups, Cg, H, W), pos.flip(-1), mode="bilinear",
+                       align_corners=True).reshape(B, C, 1, Hk * Wk)
+    out = _attend(p, xs, query, pos.reshape(B * n_groups, Hk * Wk, 2), n_heads, n_groups, H, W)
+    return F.conv2d(out, p["proj_out.weight"], p["proj_out.bias"]), pos
+
+
+def sca_forward(p, x, query, reference_points, n_heads, n_groups, bev_depth_dim,
+                scale_offset_range=True):
+    """SCADeformableAttention.forward for one view.
+    x (B,1,C,Hi,Wi); reference_points (B,1,Hq/2,Wq*D,2) in (x,y)."""
+    B, C, Hq, Wq = query.shape
+    D = bev_depth_dim
+    Cg = C // n_groups
+    Hi, Wi = x.shape[-2:]
+    ref = reference_points[:, 0].flip(-1).repeat_interleave(n_groups, 0)          # (y,x)
+    off = offset_network(p, "conv_offset_m0", query.reshape(B * n_groups, Cg, Hq, Wq), 1, 1)
+    # "(b g) d (h n) w -> (b g) n h (w d)", n=2: even query rows -> y, odd rows -> x
+    off = off.reshape(B * n_groups, D, Hq // 2, 2, Wq).permute(0, 3, 2, 4, 1)
+    off = off.reshape(B * n_groups, 2, Hq // 2, Wq * D)
+    Hk, Wk = off.shape[-2:]
+    if scale_offset_range:
+        rng = torch.tensor([1.0 / (Hk - 1.0), 1.0 / (Wk - 1.0)]).reshape(1, 2, 1, 1)
+        off = off.tanh().mul(rng).mul(5.0)
+    pos = off.permute(0, 2, 3, 1) + ref
+    if not scale_offset_range:
+        pos = pos.clamp(-1.0, 1.0)
+    xs = F.grid_sample(x[:, 0].reshape(B * n_groups, Cg, Hi, Wi), pos.flip(-1), mode="bilinear",
+                       align_corners=True).reshape(B, C, 1, Hk * Wk)
+    out = _attend(p, xs, query, pos.reshape(B * n_groups, Hk * Wk, 2), n_heads, n_groups, Hq, Wq)
+    return F.conv2d(out, p["proj_out.weight"], p["proj_out.bias"]), pos

@@ -1,0 +1,107 @@
+"""CPU tests: pin the oracle against the golden vectors made from the real reference."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import bilinear, deform_attn, msda, projection
+from util import FP32_TOL, load_golden, rel_err
+
+
+def _run_tsa(name):
+    g, p, gp = load_golden(name)
+    N, C, h, grp, k, s, B, self_attn, sor = [int(v) for v in g["cfg"]]
+    p = {k_: v.clone().requires_grad_(True) for k_, v in p.items()}
+    query = torch.from_numpy(g["query"]).requires_grad_(True)
+    x = None if self_attn else torch.from_numpy(g["x"]).requires_grad_(True)
+    out, _ = deform_attn.tsa_forward(p, x, query, h, grp, k, s, bool(sor))
+    out.backward(torch.from_numpy(g["grad_out"]))
+    return g, p, gp, out, query, x
+
+
+@pytest.mark.parametrize("name", ["tsa_s1", "tsa_s2", "tsa_self", "tsa_clamp"])
+def test_tsa_oracle_matches_reference(name):
+    g, p, gp, out, query, x = _run_tsa(name)
+    assert rel_err(out, g["out"]) < 1e-5
+    assert rel_err(query.grad, g["g_query"]) < 1e-4
+    if x is not None:
+        assert rel_err(x.grad, g["g_x"]) < 1e-4
+    for k_, ref in gp.items():
+        assert rel_err(p[k_].grad, ref) < 1e-4, k_
+    # parameters the reference never uses get no gradient
+    assert "proj_q.weight" not in gp and "proj_views.weight" not in gp
+
+
+@pytest.mark.parametrize("name", ["sca_d5", "sca_g2", "sca_clamp"])
+def test_sca_oracle_matches_reference(name):
+    g, p, gp = load_golden(name)
+    N, D, C, h, grp, B, Hi, Wi, sor = [int(v) for v in g["cfg"]]
+    p = {k_: v.clone().requires_grad_(True) for k_, v in p.items()}
+    query = torch.from_numpy(g["query"]).requires_grad_(True)
+    x = torch.from_numpy(g["x"]).requires_grad_(True)
+    out, _ = deform_attn.sca_forward(p, x, query, torch.from_numpy(g["reference_points"]), h, grp, D, bool(sor))
+    out.backward(torch.from_numpy(g["grad_out"]))
+    assert rel_err(out, g["out"]) < 1e-5
+    assert rel_err(query.grad, g["g_query"]) < 1e-4
+    assert rel_err(x.grad, g["g_x"]) < 1e-4
+    for k_, ref in gp.items():
+        assert rel_err(p[k_].grad, ref) < 1e-4, k_
+
+
+@pytest.mark.parametrize("name", ["proj_n50", "proj_n200", "proj_yaw", "proj_z0"])
+def test_projection_oracle_bit_exact(name):
+    g, _, _ = load_golden(name)
+    N, D, W, H, oW, oH = [int(v) for v in g["cfg"]]
+    bound = dict(zip("XYZ", [float(v) for v in g["bound"]]))
+    pts = projection.sample_3d_points(bound, N, D, float(g["z_shift"]))
+    assert np.array_equal(pts.numpy(), g["points"])
+    Ks = projection.scale_intrinsics(g["K"], W, H, oW, oH)
+    assert np.array_equal(Ks.numpy(), g["K_scaled"])
+    uv, pix, mask = projection.project_points(pts, g["imu_to_cam"], Ks, W, H)
+    assert np.array_equal(mask.numpy(), g["mask"])
+    assert np.array_equal(pix.numpy()[:, g["mask"]], g["pix"][:, g["mask"]])
+    assert np.array_equal(uv.numpy(), g["uv"])            # bit-exact incl. masked -> (-1,-1)
+
+
+def test_rows_equal_dense():
+    g, p, _ = load_golden("tsa_s1")
+    torch.manual_seed(0)
+    B, h, Dh, N = 2, 2, 32, 14
+    q, k, v = (torch.randn(B * h, Dh, N * N) for _ in range(3))
+    pos = deform_attn.normalized_grid(N, N).reshape(1, -1, 2).repeat(B, 1, 1) + 0.05 * torch.randn(B, N * N, 2)
+    dense = deform_attn.rpe_attention_dense(q, k, v, p["rpe_table"], pos, N, N, 1, Dh ** -0.5)
+    rows = deform_attn.rpe_attention_rows(q, k, v, p["rpe_table"], pos, N, N, 1, Dh ** -0.5, 30, 75)
+    assert torch.equal(dense[:, :, 30:75], rows)
+
+
+@pytest.mark.parametrize("align", [True, False])
+def test_numpy_bilinear_matches_grid_sample(align):
+    torch.manual_seed(1)
+    inp = torch.randn(2, 3, 7, 9, dtype=torch.float64, requires_grad=True)
+    grid = (torch.rand(2, 5, 6, 2, dtype=torch.float64) * 2.6 - 1.3).requires_grad_(True)
+    out = F.grid_sample(inp, grid, mode="bilinear", padding_mode="zeros", align_corners=align)
+    go = torch.randn_like(out)
+    out.backward(go)
+    o = bilinear.grid_sample_bilinear(inp.detach().numpy(), grid.detach().numpy(), align)
+    gi, gg = bilinear.grid_sample_bilinear_backward(go.numpy(), inp.detach().numpy(), grid.detach().numpy(), align)
+    assert np.allclose(o, out.detach().numpy(), atol=1e-12)
+    assert np.allclose(gi, inp.grad.numpy(), atol=1e-12)
+    assert np.allclose(gg, grid.grad.numpy(), atol=1e-12)
+
+
+def test_msda_oracle_matches_numpy_restatement():
+    """L>1/P>1 MSDA has no reference counterpart ("parity unpinned"): pin the grid_sample-based
+    oracle against the independent numpy restatement instead."""
+    d = msda.make_microbench_inputs(1, seed=2, n_side=8, h=2, Dh=4, L=2, P=2, sigma_px=2.0)
+    v, loc, w = d["value"].double(), d["sampling_locations"].double(), d["attention_weights"].double()
+    out = msda.msda_forward(v, d["spatial_shapes"], d["level_start_index"], loc, w)
+    B, S, h, Dh = v.shape
+    acc = np.zeros((B * h, Dh, loc.shape[1]))
+    for l, (H, W) in enumerate(d["spatial_shapes"]):
+        s0 = d["level_start_index"][l]
+        vl = v[:, s0:s0 + H * W].permute(0, 2, 3, 1).reshape(B * h, Dh, H, W).numpy()
+        gl = (2 * loc[:, :, :, l] - 1).permute(0, 2, 1, 3, 4).reshape(B * h, -1, loc.shape[4], 2).numpy()
+        wl = w[:, :, :, l].permute(0, 2, 1, 3).reshape(B * h, 1, -1, loc.shape[4]).numpy()
+        acc += (bilinear.grid_sample_bilinear(vl, gl, False) * wl).sum(-1)
+    ref = torch.from_numpy(acc).reshape(B, h * Dh, -1).transpose(1, 2)
+    assert rel_err(out, ref) < 1e-12
