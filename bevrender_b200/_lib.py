@@ -1,0 +1,63 @@
+"""ctypes binding of libbevr.so (the C ABI declared in include/bevr.h).
+
+There is no CPU fallback: if the library is missing it is built in place with
+nvcc (``make`` in csrc/), and if that fails the import raises.  The host side
+only ever passes raw device pointers + sizes across this boundary.
+"""
+import ctypes as C
+import os
+import subprocess
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libbevr.so")
+CSRC = os.path.join(_HERE, "csrc")
+
+_p, _i, _f, _z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
+
+# name -> (restype, argtypes); must list every symbol of include/bevr.h
+SIGNATURES = {
+    "bevr_version": (_i, []),
+    "bevr_last_error": (C.c_char_p, []),
+    "bevr_msda_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p] + [_i] * 10 + [_p]),
+    "bevr_msda_bwd_workspace_bytes": (_z, [_i] * 5),
+    "bevr_msda_bwd": (_i, [_p] * 11 + [_i] * 10 + [_p]),
+    "bevr_msda_set_tile": (None, [_i] * 3),
+    "bevr_project_points": (_i, [_p] * 6 + [_i] * 3 + [_p]),
+    "bevr_rpe_attn_fwd": (_i, [_p] * 7 + [_i] * 9 + [_f, _p]),
+    "bevr_rpe_attn_bwd": (_i, [_p] * 14 + [_i] * 9 + [_f, _p]),
+}
+
+
+def build(force=False):
+    """Compile csrc/*.cu for sm_100a into libbevr.so (nvcc cross-compiles without a GPU)."""
+    if force:
+        subprocess.run(["make", "-C", CSRC, "clean"], check=True, capture_output=True)
+    r = subprocess.run(["make", "-C", CSRC, "-j8"], capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libbevr.so failed:\n" + r.stdout[-4000:] + r.stderr[-4000:])
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            build()
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)          # AttributeError if the .so lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        _lib = handle
+    return _lib
+
+
+class BevrError(RuntimeError):
+    pass
+
+
+def check(rc, what):
+    if rc != 0:
+        raise BevrError(f"{what} failed (rc={rc}): {lib().bevr_last_error().decode()}")

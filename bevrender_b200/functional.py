@@ -1,0 +1,137 @@
+"""Host-side operators of the hot path: thin torch.autograd wrappers over the C ABI.
+
+Every operator requires CUDA tensors and raises otherwise -- there is no CPU
+fallback (the CPU restatement lives in ``oracle/`` and is test-only).
+"""
+import ctypes as C
+import functools
+
+import torch
+
+from . import _lib
+
+F32, BF16 = 0, 1
+ALIGN_CORNERS, LOC_PM1, OFFSET_PIXELS, ACCUMULATE = 1, 2, 4, 8
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+def _ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("bevrender_b200 operators run on CUDA tensors only (no CPU fallback)")
+
+
+@functools.lru_cache(maxsize=256)
+def _levels(shapes, starts):
+    hw = (C.c_int32 * (2 * len(shapes)))(*[int(v) for s in shapes for v in s])
+    st = (C.c_int32 * len(starts))(*[int(v) for v in starts])
+    return hw, st
+
+
+def _as_tuple(x, pair=False):
+    if torch.is_tensor(x):
+        x = x.tolist()            # a CUDA tensor syncs here: pass CPU tensors / lists instead
+    return tuple(tuple(int(v) for v in r) for r in x) if pair else tuple(int(v) for v in x)
+
+
+class _MSDA(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, value, loc, weight, ref, shapes, starts, query_w, flags):
+        _need_cuda(value, loc, weight, ref)
+        B, S, h, Dh = value.shape
+        _, Nq, _, L, P, _ = loc.shape
+        dt = _DTYPES[value.dtype]
+        value, loc = value.contiguous(), loc.contiguous().float()
+        weight = None if weight is None else weight.contiguous().to(value.dtype)
+        ref = None if ref is None else ref.contiguous().float()
+        out = torch.empty(B, Nq, h * Dh, dtype=value.dtype, device=value.device)
+        hw, st = _levels(shapes, starts)
+        _lib.check(_lib.lib().bevr_msda_fwd(_ptr(value), hw, st, _ptr(loc), _ptr(ref), _ptr(weight), _ptr(out),
+                                            B, S, h, Dh, Nq, L, P, query_w, dt, flags, _stream()), "bevr_msda_fwd")
+        ctx.save_for_backward(value, loc, weight, ref)
+        ctx.meta = (shapes, starts, query_w, flags, dt)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        value, loc, weight, ref = ctx.saved_tensors
+        shapes, starts, query_w, flags, dt = ctx.meta
+        B, S, h, Dh = value.shape
+        _, Nq, _, L, P, _ = loc.shape
+        need_v, need_l, need_w, need_r = ctx.needs_input_grad[:4]
+        grad_out = grad_out.contiguous().to(value.dtype)
+        gv = torch.empty_like(value) if need_v else None
+        gl = torch.empty_like(loc) if (need_l or need_r) else None
+        gw = torch.empty_like(weight) if (need_w and weight is not None) else None
+        ws = None
+        nws = _lib.lib().bevr_msda_bwd_workspace_bytes(B, S, h, Dh, dt)
+        if need_v and nws:
+            ws = torch.empty(nws, dtype=torch.uint8, device=value.device)
+        hw, st = _levels(shapes, starts)
+        _lib.check(_lib.lib().bevr_msda_bwd(_ptr(value), hw, st, _ptr(loc), _ptr(ref), _ptr(weight), _ptr(grad_out),
+                                            _ptr(gv), _ptr(gl), _ptr(gw), _ptr(ws), B, S, h, Dh, Nq, L, P,
+                                            query_w, dt, flags, _stream()), "bevr_msda_bwd")
+        gr = None
+        if need_r:                      # loc = ref + off * s  ->  d/d ref = sum over heads and points
+            gr = gl.sum(dim=(2, 4))
+        if gl is not None and ref is not None and (flags & OFFSET_PIXELS):
+            wh = torch.tensor([[w, hh] for hh, w in shapes], dtype=gl.dtype, device=gl.device)
+            gl = gl / wh[None, None, None, :, None, :]
+        return gv, (gl if need_l else None), gw, gr, None, None, None, None
+
+
+def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights=None,
+                   reference_points=None, query_w=0, align_corners=False, loc_pm1=False,
+                   offset_in_pixels=False):
+    """Multi-scale deformable attention gather (kernels K1/K2).
+
+    value (B,S,h,Dh) fp32|bf16 channels-last; sampling_locations (B,Nq,h,L,P,2) fp32 (x,y) --
+    or sampling OFFSETS when ``reference_points`` (B,Nq,L,2) is given (loc = ref + off, with
+    off / (W_l,H_l) if ``offset_in_pixels``); attention_weights (B,Nq,h,L,P) or None (== 1).
+    Returns (B, Nq, h*Dh).  ``query_w``: width of the 2-D query grid (enables 2-D tiling).
+    """
+    flags = (ALIGN_CORNERS if align_corners else 0) | (LOC_PM1 if loc_pm1 else 0) | \
+            (OFFSET_PIXELS if offset_in_pixels else 0)
+    shapes = _as_tuple(spatial_shapes, pair=True)
+    starts = _as_tuple(level_start_index)
+    return _MSDA.apply(value, sampling_locations, attention_weights, reference_points, shapes, starts,
+                       int(query_w), flags)
+
+
+def grid_gather(x, pos_yx):
+    """The reference's own gather: ``F.grid_sample(x, pos[..., (1,0)], bilinear, align_corners=True)``
+    (TSA_deform_attn.py:210-217, SCA_deform_attn.py:290-301) as MSDA with L = P = 1 and unit weights.
+
+    x (N, C, H, W) NCHW; pos_yx (N, Hk, Wk, 2) in (y, x) -> (N, C, Hk*Wk).
+    """
+    N, Cc, H, W = x.shape
+    Hk, Wk = pos_yx.shape[1:3]
+    value = x.permute(0, 2, 3, 1).reshape(N, H * W, 1, Cc)
+    loc = pos_yx.flip(-1).reshape(N, Hk * Wk, 1, 1, 1, 2)
+    out = ms_deform_attn(value, ((H, W),), (0,), loc, None, query_w=Wk, align_corners=True, loc_pm1=True)
+    return out.transpose(1, 2)
+
+
+def project_points(points, cam_T, K, img_w, img_h):
+    """K4: points (4, ...) fp32 CUDA; cam_T = inverse(imu_to_cam) 4x4 and K 3x3 as CPU tensors.
+    Returns uv (2, ...) in [-1,1] (masked -> -1), pix (2, ...) int32, mask (...) bool."""
+    _need_cuda(points)
+    shp = points.shape[1:]
+    p = points.reshape(4, -1).contiguous().float()
+    n = p.shape[1]
+    uv = torch.empty(2, n, dtype=torch.float32, device=p.device)
+    pix = torch.empty(2, n, dtype=torch.int32, device=p.device)
+    mask = torch.empty(n, dtype=torch.uint8, device=p.device)
+    T = (C.c_float * 16)(*torch.as_tensor(cam_T, dtype=torch.float32).reshape(-1).tolist())
+    Kc = (C.c_float * 9)(*torch.as_tensor(K, dtype=torch.float32)[:, :3].reshape(-1).tolist())
+    _lib.check(_lib.lib().bevr_project_points(_ptr(p), T, Kc, _ptr(uv), _ptr(pix), _ptr(mask), n,
+                                              int(img_w), int(img_h), _stream()), "bevr_project_points")
+    return uv.reshape(2, *shp), pix.reshape(2, *shp), mask.bool().reshape(*shp)

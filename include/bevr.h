@@ -1,0 +1,137 @@
+/* bevr.h -- C ABI of libbevr.so, the sm_100a implementation of BEVRender's
+ * deformable-attention hot path (rpl-cmu/bevrender; citations are file:line in
+ * the reference checkout).
+ *
+ * Conventions
+ *  - The reference is pure Python/PyTorch; what it "binds" for this path are
+ *    torch library calls.  Each entry point below names the reference call
+ *    sites it replaces.  The Python host side (bevrender_b200/) loads this
+ *    library with ctypes and passes raw device pointers of torch tensors.
+ *  - Ownership: the caller allocates every input, output and workspace buffer.
+ *    The library never allocates, frees or retains device memory.
+ *  - Every function only ENQUEUES work on `stream` (a cudaStream_t; NULL is the
+ *    legacy default stream) on the caller's current device.  No implicit
+ *    synchronisation, no global mutable state; re-entrant.
+ *  - Return value: 0 success; <0 argument validation error; >0 a cudaError_t
+ *    raised at launch.  bevr_last_error() returns a thread-local message.
+ *  - dtype: 0 = float32, 1 = bfloat16 (storage of value/out/weights/grads;
+ *    coordinates and accumulators are always float32).
+ *  - "host" pointers are read during the call (copied into kernel params).
+ */
+#ifndef BEVR_H_
+#define BEVR_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BEVR_VERSION 100
+
+enum { BEVR_F32 = 0, BEVR_BF16 = 1 };
+
+/* coordinate / behaviour flags */
+enum {
+  BEVR_ALIGN_CORNERS   = 1,  /* pixel = u*(size-1) instead of u*size-0.5 (F.grid_sample align_corners) */
+  BEVR_LOC_PM1         = 2,  /* locations are grid_sample grids in [-1,1]; else in [0,1]               */
+  BEVR_OFFSET_PIXELS   = 4,  /* with ref_points: loc = ref + off / (W_l, H_l); else loc = ref + off    */
+  BEVR_ACCUMULATE      = 8   /* bwd: add into grad_value instead of zero-filling it first              */
+};
+
+#define BEVR_MAX_LEVELS 8
+
+int bevr_version(void);
+const char* bevr_last_error(void);
+
+/* ---------------------------------------------------------------------------
+ * K1  multi-scale deformable-attention gather, forward.
+ * Replaces F.grid_sample at TSA_deform_attn.py:210-217 and
+ * SCA_deform_attn.py:290-301 (L=1, P=1, attn_weight=NULL, BEVR_LOC_PM1 |
+ * BEVR_ALIGN_CORNERS) and implements the general operator of the north star
+ * (query/value/reference_points/spatial_shapes/level_start_index/
+ * sampling_offsets/attention_weights).
+ *   value        dev  dtype  (B, S, h, Dh)          channels-last, S = sum H_l*W_l
+ *   spatial_hw   host int32  (L, 2)  rows (H_l, W_l)
+ *   level_start  host int32  (L)
+ *   sampling_loc dev  f32    (B, Nq, h, L, P, 2)    (x, y); offsets if ref_points != NULL
+ *   ref_points   dev  f32    (B, Nq, L, 2) or NULL
+ *   attn_weight  dev  dtype  (B, Nq, h, L, P) or NULL (all ones)
+ *   out          dev  dtype  (B, Nq, h*Dh)
+ *   query_w      width of the 2-D query grid (queries are tiled 2-D for cache
+ *                locality) or 0 for a flat query list.
+ * Requires Dh * sizeof(dtype) to be a multiple of 16 bytes.
+ */
+int bevr_msda_fwd(const void* value, const int32_t* spatial_hw, const int32_t* level_start,
+                  const float* sampling_loc, const float* ref_points, const void* attn_weight,
+                  void* out, int B, int S, int h, int Dh, int Nq, int L, int P, int query_w,
+                  int dtype, int flags, void* stream);
+
+/* K2  backward of K1 (replaces the autograd of the grid_sample calls above).
+ *   grad_out     dev  dtype  (B, Nq, h*Dh)
+ *   grad_value   dev  dtype  (B, S, h, Dh) or NULL (skip: TSA trains with a
+ *                            detached prev_bev, bevrender.py:125-133)
+ *   grad_loc     dev  f32    (B, Nq, h, L, P, 2) or NULL   (d/d sampling_loc)
+ *   grad_weight  dev  dtype  (B, Nq, h, L, P) or NULL
+ *   workspace    dev  f32    bevr_msda_bwd_workspace_bytes() bytes; only used
+ *                            for dtype=bf16 with grad_value (fp32 accumulation)
+ */
+size_t bevr_msda_bwd_workspace_bytes(int B, int S, int h, int Dh, int dtype);
+int bevr_msda_bwd(const void* value, const int32_t* spatial_hw, const int32_t* level_start,
+                  const float* sampling_loc, const float* ref_points, const void* attn_weight,
+                  const void* grad_out, void* grad_value, float* grad_loc, void* grad_weight,
+                  void* workspace, int B, int S, int h, int Dh, int Nq, int L, int P, int query_w,
+                  int dtype, int flags, void* stream);
+
+/* Tuning hook for benchmark sweeps (process-wide, not thread-safe; zeros restore the defaults):
+ * query-tile shape and CTA size used by K1/K2. */
+void bevr_msda_set_tile(int tile_w, int tile_h, int threads);
+
+/* ---------------------------------------------------------------------------
+ * K4  camera -> BEV reference-point projection.
+ * Replaces BEV2CameraProjector.bev_grid_to_camera + get_in_bound_mask
+ * (bev_cmr_proj.py:61-124, remove_ref_in_gray=False), bit-exact with the
+ * reference's torch-CPU result.
+ *   points   dev f32 (4, n)  homogeneous IMU-frame points (SCA.py:112-162)
+ *   cam_T    host f32 (16)   row-major inverse(imu_to_cam)  (inverse stays on the host)
+ *   K        host f32 (9)    row-major intrinsics K[:, :3], already scaled to the image size
+ *   uv       dev f32 (2, n)  normalised (x, y) in [-1,1]; masked points -> (-1,-1)
+ *   pix      dev i32 (2, n)  or NULL: truncated pixel indices (x86 cvtt semantics)
+ *   mask     dev u8  (n)     or NULL: 1 = inside [0,W-1) x [0,H-1)
+ */
+int bevr_project_points(const float* points, const float* cam_T, const float* K, float* uv,
+                        int32_t* pix, uint8_t* mask, int n, int img_w, int img_h, void* stream);
+
+/* ---------------------------------------------------------------------------
+ * K3  fused attention with sampled relative-position bias (flash style; the
+ * (Nq, Ns) matrix is never materialised).
+ * Replaces einsum/mul/grid_sample/softmax/einsum at TSA_deform_attn.py:245-330
+ * and SCA_deform_attn.py:331-411.
+ *   q        dev f32 (BH, Dh, Nq)     BH = B*h, channel-major as the reference reshapes NCHW
+ *   k, v     dev f32 (BH, Dh, Ns)
+ *   rpe      dev f32 (h, Rh, Rw)      rpe_table; Rh = 2*Hq-1, Rw arbitrary (2*Wq-1 or 2*Wq*D-1)
+ *   pos      dev f32 (BH/hpg, Ns, 2)  key positions (y, x) in grid_sample units
+ *   out      dev f32 (BH, Dh, Nq)
+ *   lse      dev f32 (BH, Nq)         log-sum-exp per row (saved for backward)
+ *   hpg      heads per group (head bh uses pos[bh / hpg], table rpe[bh % h])
+ * Requires Dh == 32 or 64 (the reference uses 32 everywhere, encoder.py:23-39).
+ */
+int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe,
+                      const float* pos, float* out, float* lse, int BH, int h, int hpg, int Dh,
+                      int Hq, int Wq, int Ns, int Rh, int Rw, float scale, void* stream);
+
+/* Backward of K3.  grad_rpe (h,Rh,Rw) and grad_pos (BH/hpg,Ns,2) are ACCUMULATED into
+ * (caller zero-fills); grad_q/grad_k/grad_v are overwritten.  Any grad pointer may be NULL.
+ *   delta_ws dev f32 (BH, Nq) workspace (row-wise sum(dO*O)).
+ */
+int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v, const float* rpe,
+                      const float* pos, const float* out, const float* lse, const float* grad_out,
+                      float* grad_q, float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos,
+                      float* delta_ws, int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns,
+                      int Rh, int Rw, float scale, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BEVR_H_ */

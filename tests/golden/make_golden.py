@@ -137,7 +137,7 @@ def make_proj(name, N, D, bound, z_shift, yaw_deg, pitch_deg, img_w=160, img_h=1
         cfg=np.array([N, D, img_w, img_h, 640, 512]), bound=np.array([bound["X"], bound["Y"], bound["Z"]]),
         z_shift=np.array(z_shift), imu_to_cam=T, K=K, points=pts.numpy(), uv=uv.numpy(),
         mask=mask.reshape(pts.shape[1:]).numpy(), pix=raw.to(torch.int32).reshape(2, *pts.shape[1:]).numpy(),
-        K_scaled=proj.K[0][0].numpy())
+        K_scaled=proj.K[0][0].numpy(), cam_T=proj.imu_to_cmr[0][0].inverse().numpy())
     print(name, "points", tuple(pts.shape), "valid", float(mask.float().mean()))
     return uv
 

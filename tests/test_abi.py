@@ -1,0 +1,63 @@
+"""CPU tests of the drop-in boundary: libbevr.so loads and exports every symbol of include/bevr.h;
+argument validation works without a GPU (no kernel is launched)."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_symbols():
+    src = open(os.path.join(ROOT, "include", "bevr.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(bevr_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_path():
+    syms = header_symbols()
+    for s in ("bevr_msda_fwd", "bevr_msda_bwd", "bevr_project_points", "bevr_rpe_attn_fwd",
+              "bevr_rpe_attn_bwd", "bevr_last_error", "bevr_version"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol():
+    from bevrender_b200 import _lib
+    handle = C.CDLL(_lib.LIB_PATH) if os.path.exists(_lib.LIB_PATH) else C.CDLL(_lib.build())
+    for s in header_symbols():
+        assert hasattr(handle, s), f"libbevr.so lacks {s}"
+    assert set(header_symbols()) == set(_lib.SIGNATURES), "ctypes table and header disagree"
+    assert _lib.lib().bevr_version() == 100
+
+
+def test_argument_validation_returns_negative_and_message():
+    from bevrender_b200 import _lib
+    L = _lib.lib()
+    hw = (C.c_int32 * 2)(4, 4)
+    st = (C.c_int32 * 1)(0)
+    # Dh=6 fp32 is not a multiple of 16 bytes -> rejected before any CUDA call
+    rc = L.bevr_msda_fwd(None, hw, st, None, None, None, None, 1, 16, 1, 6, 4, 1, 1, 0, 0, 0, None)
+    assert rc < 0 and b"16 bytes" in L.bevr_last_error()
+    rc = L.bevr_msda_fwd(None, hw, st, None, None, None, None, 1, 8, 1, 4, 4, 1, 1, 0, 0, 0, None)
+    assert rc < 0 and b"outside S" in L.bevr_last_error()
+    rc = L.bevr_project_points(None, None, None, None, None, None, 4, 160, 128, None)
+    assert rc < 0
+
+
+def test_operators_refuse_cpu_tensors():
+    import torch
+    import bevrender_b200 as bb
+    v = torch.zeros(1, 16, 1, 4)
+    loc = torch.zeros(1, 4, 1, 1, 1, 2)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        bb.ms_deform_attn(v, [(4, 4)], [0], loc)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "bevrender_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f

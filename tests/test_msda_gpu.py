@@ -1,0 +1,148 @@
+"""GPU parity tests of K1/K2 (MSDA gather fwd/bwd) through the C ABI against the oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import msda as omsda
+from util import BF16_TOL, FP32_TOL, load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+
+def _run_cuda(d, dtype, align, pm1, need_value=True):
+    import bevrender_b200 as bb
+    dev = "cuda"
+    value = d["value"].to(dev).to(dtype).requires_grad_(need_value)
+    loc = d["sampling_locations"].to(dev).requires_grad_(True)
+    w = d["attention_weights"]
+    w = None if w is None else w.to(dev).to(dtype).requires_grad_(True)
+    out = bb.ms_deform_attn(value, d["spatial_shapes"], d["level_start_index"], loc, w,
+                            query_w=d.get("query_w", 0), align_corners=align, loc_pm1=pm1)
+    out.backward(d["grad_out"].to(dev).to(dtype))
+    return out, value.grad, loc.grad, (None if w is None else w.grad)
+
+
+def _check(d, dtype, align=False, pm1=False, tol=None):
+    tol = tol or (FP32_TOL if dtype == torch.float32 else BF16_TOL)
+    out, gv, gl, gw = _run_cuda(d, dtype, align, pm1)
+    # oracle in fp32 on the (possibly bf16-rounded) inputs the kernel saw
+    cast = lambda t: None if t is None else t.to(dtype).float()
+    ref = omsda.msda_forward_backward(cast(d["value"]), d["spatial_shapes"], d["level_start_index"],
+                                      d["sampling_locations"], cast(d["attention_weights"]), cast(d["grad_out"]),
+                                      align, pm1)
+    names = ("out", "grad_value", "grad_loc", "grad_weight")
+    for n, a, b in zip(names, (out, gv, gl, gw), ref):
+        if b is None:
+            assert a is None
+            continue
+        e = rel_err(a.float().cpu(), b)
+        assert e < tol, f"{n}: rel err {e:.3e} >= {tol}"
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("align,pm1", [(False, False), (True, False), (True, True), (False, True)])
+def test_msda_small_all_coordinate_modes(dtype, align, pm1):
+    d = omsda.make_microbench_inputs(2, seed=1, n_side=24, h=4, Dh=32, L=3, P=4, sigma_px=2.0)
+    if pm1:
+        d["sampling_locations"] = d["sampling_locations"] * 2 - 1
+    _check(d, dtype, align, pm1)
+
+
+@pytest.mark.parametrize("h,Dh,L,P", [(1, 4, 1, 1), (2, 8, 2, 3), (3, 16, 1, 5), (8, 32, 4, 4), (2, 64, 2, 2),
+                                       (1, 128, 1, 1), (1, 256, 1, 2), (5, 48, 2, 1)])
+def test_msda_shapes_fp32(h, Dh, L, P):
+    d = omsda.make_microbench_inputs(1, seed=3, n_side=16, h=h, Dh=Dh, L=L, P=P, sigma_px=3.0)
+    _check(d, torch.float32)
+
+
+@pytest.mark.parametrize("h,Dh,L,P", [(2, 8, 2, 3), (8, 32, 4, 4), (2, 64, 2, 2), (1, 256, 1, 1)])
+def test_msda_shapes_bf16(h, Dh, L, P):
+    d = omsda.make_microbench_inputs(1, seed=4, n_side=16, h=h, Dh=Dh, L=L, P=P, sigma_px=3.0)
+    _check(d, torch.bfloat16)
+
+
+def test_msda_flat_queries_ragged_and_out_of_range():
+    """Flat query list (query_w = 0), Nq not a multiple of the tile, locations far outside the map,
+    NaN location: out-of-range taps contribute zero, as grid_sample(padding_mode='zeros')."""
+    d = omsda.make_microbench_inputs(1, seed=5, n_side=10, h=2, Dh=8, L=2, P=2, sigma_px=1.0)
+    d["query_w"] = 0
+    Nq = 77
+    for k in ("sampling_locations", "attention_weights", "grad_out"):
+        d[k] = d[k][:, :Nq].contiguous()
+    d["sampling_locations"][0, :5] = 7.5          # far outside
+    d["sampling_locations"][0, 5:9] = -3.0
+    d["sampling_locations"][0, 9, 0, 0, 0, 0] = 1.0     # exactly on the border
+    _check(d, torch.float32)
+    import bevrender_b200 as bb
+    loc = d["sampling_locations"].clone()
+    loc[0, 11] = float("nan")
+    out = bb.ms_deform_attn(d["value"].cuda(), d["spatial_shapes"], d["level_start_index"], loc.cuda(),
+                            d["attention_weights"].cuda())
+    assert torch.isfinite(out).all() and out[0, 11].abs().max() == 0
+
+
+def test_reference_gather_l1p1_matches_grid_sample():
+    """The reference's own use: grid_sample(align_corners=True) on an NCHW map with (y,x) positions."""
+    import bevrender_b200 as bb
+    torch.manual_seed(0)
+    x = torch.randn(3, 64, 14, 18, requires_grad=True)
+    pos = (torch.rand(3, 7, 30, 2) * 2.4 - 1.2).requires_grad_(True)
+    ref = F.grid_sample(x, pos.flip(-1), mode="bilinear", align_corners=True).reshape(3, 64, -1)
+    g = torch.randn_like(ref)
+    ref.backward(g)
+    xc = x.detach().cuda().requires_grad_(True)
+    pc = pos.detach().cuda().requires_grad_(True)
+    out = bb.grid_gather(xc, pc)
+    out.backward(g.cuda())
+    assert rel_err(out.cpu(), ref) < FP32_TOL
+    assert rel_err(xc.grad.cpu(), x.grad) < FP32_TOL
+    assert rel_err(pc.grad.cpu(), pos.grad) < FP32_TOL
+
+
+def test_reference_points_plus_offsets_fused():
+    import bevrender_b200 as bb
+    d = omsda.make_microbench_inputs(1, seed=6, n_side=12, h=2, Dh=16, L=2, P=2)
+    B, Nq, h, L, P, _ = d["sampling_locations"].shape
+    ref_pts = torch.rand(B, Nq, L, 2)
+    off = torch.randn(B, Nq, h, L, P, 2) * 2.0
+    loc = omsda.locations_from_offsets(ref_pts, off, d["spatial_shapes"], True)
+    exp = omsda.msda_forward_backward(d["value"], d["spatial_shapes"], d["level_start_index"], loc,
+                                      d["attention_weights"], d["grad_out"])
+    offc = off.cuda().requires_grad_(True)
+    refc = ref_pts.cuda().requires_grad_(True)
+    out = bb.ms_deform_attn(d["value"].cuda(), d["spatial_shapes"], d["level_start_index"], offc,
+                            d["attention_weights"].cuda(), reference_points=refc, query_w=12, offset_in_pixels=True)
+    out.backward(d["grad_out"].cuda())
+    assert rel_err(out.cpu(), exp[0]) < FP32_TOL
+    wh = torch.tensor([[w, hh] for hh, w in d["spatial_shapes"]]).reshape(1, 1, 1, L, 1, 2)
+    assert rel_err(offc.grad.cpu(), exp[2] / wh) < FP32_TOL
+    assert rel_err(refc.grad.cpu(), exp[2].sum(dim=(2, 4))) < FP32_TOL
+
+
+def test_full_size_properties():
+    """BASELINE.json config 2 shape (200x200 queries, 4 levels, 8 heads, 4 points, B=1):
+    size-independent properties instead of an oracle run -- linearity in value, weights summing to
+    one reproduce a constant map, and sum(grad_value) == sum over queries of weighted grad_out."""
+    import bevrender_b200 as bb
+    d = omsda.make_microbench_inputs(1, seed=0)
+    dev = "cuda"
+    v = d["value"].to(dev)
+    loc, w = d["sampling_locations"].to(dev), d["attention_weights"].to(dev)
+    args = (d["spatial_shapes"], d["level_start_index"])
+    f = lambda val: bb.ms_deform_attn(val, *args, loc, w, query_w=200)
+    o1, o2 = f(v), f(2.5 * v)
+    assert rel_err(o2.cpu(), 2.5 * o1.cpu()) < 1e-6
+    # interior queries (all taps in range) of a constant map return the constant
+    ones = torch.ones_like(v)
+    oc = f(ones).reshape(200, 200, -1)[40:160, 40:160]
+    assert (oc - 1).abs().max() < 1e-5
+    vg = v.clone().requires_grad_(True)
+    go = d["grad_out"].to(dev)
+    f(vg).backward(go)
+    lhs = vg.grad.double().sum()
+    rhs = (f(ones).double() * go.double()).sum()       # <grad_value, 1> == <grad_out, f(1)>
+    assert abs(float(lhs - rhs)) / abs(float(rhs)) < 1e-5
+    # subset parity against the oracle on a 16-row band of queries
+    band = slice(96 * 200, 112 * 200)
+    ref = omsda.msda_forward(d["value"], *args, d["sampling_locations"][:, band], d["attention_weights"][:, band])
+    assert rel_err(o1[:, band].cpu(), ref) < FP32_TOL
