@@ -86,9 +86,10 @@ class ClockSampler:
 def cpu_reference_step(B_sample, dtype_name, threads):
     """One fwd+bwd of the CPU oracle (grid_sample-based MSDA, the construction the reference uses)
     on B_sample samples of the config-2 workload.  Returns seconds."""
-    from oracle import msda as omsda
+    from bevrender_b200.workloads import make_microbench_inputs
+    from oracle import msda as omsda          # cpu_baseline / --impl reference leg only
     torch.set_num_threads(threads)
-    d = omsda.make_microbench_inputs(B_sample, seed=0)
+    d = make_microbench_inputs(B_sample, seed=0)
     t0 = time.perf_counter()
     omsda.msda_forward_backward(d["value"], d["spatial_shapes"], d["level_start_index"], d["sampling_locations"],
                                 d["attention_weights"], d["grad_out"])
@@ -154,7 +155,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
 
     from bevrender_b200 import _lib
-    from oracle import msda as omsda   # input factory only (shapes of config 2)
+    from bevrender_b200.workloads import make_microbench_inputs
     L = _lib.lib()
     if args.tile:
         tw, th, thr = [int(v) for v in args.tile.split(",")]
@@ -166,7 +167,7 @@ def main():
     warm = max(args.warmup, 3)
 
     # ---- synthetic inputs (pinned host copies for the e2e leg, device copies for the kernel leg)
-    host = omsda.make_microbench_inputs(B, seed=rank, dtype=tdt)
+    host = make_microbench_inputs(B, seed=rank, dtype=tdt)
     shapes, starts = host["spatial_shapes"], host["level_start_index"]
     S = sum(h * w for h, w in shapes)
     Nq = N_SIDE * N_SIDE

@@ -4,6 +4,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import msda as omsda
+from bevrender_b200.workloads import make_microbench_inputs
 from util import BF16_TOL, FP32_TOL, load_golden, rel_err
 
 pytestmark = pytest.mark.gpu
@@ -42,7 +43,7 @@ def _check(d, dtype, align=False, pm1=False, tol=None):
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("align,pm1", [(False, False), (True, False), (True, True), (False, True)])
 def test_msda_small_all_coordinate_modes(dtype, align, pm1):
-    d = omsda.make_microbench_inputs(2, seed=1, n_side=24, h=4, Dh=32, L=3, P=4, sigma_px=2.0)
+    d = make_microbench_inputs(2, seed=1, n_side=24, h=4, Dh=32, L=3, P=4, sigma_px=2.0)
     if pm1:
         d["sampling_locations"] = d["sampling_locations"] * 2 - 1
     _check(d, dtype, align, pm1)
@@ -51,20 +52,20 @@ def test_msda_small_all_coordinate_modes(dtype, align, pm1):
 @pytest.mark.parametrize("h,Dh,L,P", [(1, 4, 1, 1), (2, 8, 2, 3), (3, 16, 1, 5), (8, 32, 4, 4), (2, 64, 2, 2),
                                        (1, 128, 1, 1), (1, 256, 1, 2), (5, 48, 2, 1)])
 def test_msda_shapes_fp32(h, Dh, L, P):
-    d = omsda.make_microbench_inputs(1, seed=3, n_side=16, h=h, Dh=Dh, L=L, P=P, sigma_px=3.0)
+    d = make_microbench_inputs(1, seed=3, n_side=16, h=h, Dh=Dh, L=L, P=P, sigma_px=3.0)
     _check(d, torch.float32)
 
 
 @pytest.mark.parametrize("h,Dh,L,P", [(2, 8, 2, 3), (8, 32, 4, 4), (2, 64, 2, 2), (1, 256, 1, 1)])
 def test_msda_shapes_bf16(h, Dh, L, P):
-    d = omsda.make_microbench_inputs(1, seed=4, n_side=16, h=h, Dh=Dh, L=L, P=P, sigma_px=3.0)
+    d = make_microbench_inputs(1, seed=4, n_side=16, h=h, Dh=Dh, L=L, P=P, sigma_px=3.0)
     _check(d, torch.bfloat16)
 
 
 def test_msda_flat_queries_ragged_and_out_of_range():
     """Flat query list (query_w = 0), Nq not a multiple of the tile, locations far outside the map,
     NaN location: out-of-range taps contribute zero, as grid_sample(padding_mode='zeros')."""
-    d = omsda.make_microbench_inputs(1, seed=5, n_side=10, h=2, Dh=8, L=2, P=2, sigma_px=1.0)
+    d = make_microbench_inputs(1, seed=5, n_side=10, h=2, Dh=8, L=2, P=2, sigma_px=1.0)
     d["query_w"] = 0
     Nq = 77
     for k in ("sampling_locations", "attention_weights", "grad_out"):
@@ -101,7 +102,7 @@ def test_reference_gather_l1p1_matches_grid_sample():
 
 def test_reference_points_plus_offsets_fused():
     import bevrender_b200 as bb
-    d = omsda.make_microbench_inputs(1, seed=6, n_side=12, h=2, Dh=16, L=2, P=2)
+    d = make_microbench_inputs(1, seed=6, n_side=12, h=2, Dh=16, L=2, P=2)
     B, Nq, h, L, P, _ = d["sampling_locations"].shape
     ref_pts = torch.rand(B, Nq, L, 2)
     off = torch.randn(B, Nq, h, L, P, 2) * 2.0
@@ -124,7 +125,7 @@ def test_full_size_properties():
     size-independent properties instead of an oracle run -- linearity in value, weights summing to
     one reproduce a constant map, and sum(grad_value) == sum over queries of weighted grad_out."""
     import bevrender_b200 as bb
-    d = omsda.make_microbench_inputs(1, seed=0)
+    d = make_microbench_inputs(1, seed=0)
     dev = "cuda"
     v = d["value"].to(dev)
     loc, w = d["sampling_locations"].to(dev), d["attention_weights"].to(dev)

@@ -5,6 +5,7 @@ import torch
 import torch.nn.functional as F
 
 from oracle import bilinear, deform_attn, msda, projection
+from bevrender_b200.workloads import make_microbench_inputs
 from util import FP32_TOL, load_golden, rel_err
 
 
@@ -92,7 +93,7 @@ def test_numpy_bilinear_matches_grid_sample(align):
 def test_msda_oracle_matches_numpy_restatement():
     """L>1/P>1 MSDA has no reference counterpart ("parity unpinned"): pin the grid_sample-based
     oracle against the independent numpy restatement instead."""
-    d = msda.make_microbench_inputs(1, seed=2, n_side=8, h=2, Dh=4, L=2, P=2, sigma_px=2.0)
+    d = make_microbench_inputs(1, seed=2, n_side=8, h=2, Dh=4, L=2, P=2, sigma_px=2.0)
     v, loc, w = d["value"].double(), d["sampling_locations"].double(), d["attention_weights"].double()
     out = msda.msda_forward(v, d["spatial_shapes"], d["level_start_index"], loc, w)
     B, S, h, Dh = v.shape
