@@ -4,6 +4,8 @@ Host side: Python/PyTorch (device memory, streams, torch.distributed).  Compute:
 CUDA behind the C ABI of ``include/bevr.h`` (``libbevr.so``, loaded with ctypes).
 """
 from . import _lib
-from .functional import grid_gather, ms_deform_attn, project_points
+from .bev_cmr_proj import BEV2CameraProjector
+from .deform_attn import SCADeformableAttention, TSADeformableAttention
+from .functional import grid_gather, ms_deform_attn, project_points, rpe_attention
 
-__all__ = ["ms_deform_attn", "grid_gather", "project_points", "_lib"]
+__all__ = ["TSADeformableAttention", "SCADeformableAttention", "BEV2CameraProjector", "ms_deform_attn", "grid_gather", "project_points", "rpe_attention", "_lib"]

@@ -1,13 +1,364 @@
-// K3 placeholder while the fused kernel is being written (replaced in the next commit).
+// K3: fused attention with sampled relative-position bias, forward and backward (sm_100a).
+//
+// Replaces, per (batch, head):   attn = (q^T k) * scale                      TSA_deform_attn.py:245-250
+//                                bias = grid_sample(rpe_table, (qgrid_i - pos_j)/2)        :264-305
+//                                out  = softmax_j(attn + bias) v^T                          :308-330
+// (same code at SCA_deform_attn.py:331-411).  The reference materialises attn, bias and the
+// displacement tensor at (Nq, Ns); here nothing of size Nq*Ns ever exists: one thread owns one
+// query row (forward, dQ) or one key column (dK/dV/dpos/drpe), K/V (resp. Q/dO) tiles are staged
+// in shared memory and broadcast to the warp, the bias is a bilinear lookup computed on the fly
+// from the query index and the staged key position, and the softmax is the online (flash) form.
+// All arithmetic is fp32 FFMA on the CUDA cores (the 1e-4 tolerance rules out tf32/bf16 tensor
+// cores; Dh = 32 is small).
+#include <math.h>
+
 #include "bevr_common.cuh"
-extern "C" int bevr_rpe_attn_fwd(const float*, const float*, const float*, const float*, const float*, float*, float*,
-                                 int, int, int, int, int, int, int, int, int, float, void*) {
-  bevr::set_error("rpe_attn_fwd: not built into this library yet");
-  return -2;
+
+namespace bevr {
+
+struct RpeArgs {
+  const float *q, *k, *v, *rpe, *pos, *out, *lse, *grad_out, *delta;
+  float *o_out, *o_lse, *grad_q, *grad_k, *grad_v, *grad_rpe, *grad_pos, *o_delta;
+  int BH, h, hpg, Hq, Wq, Nq, Ns, Rh, Rw;
+  float scale;
+};
+
+constexpr int DH = 32;
+constexpr int PAD = DH + 4;   // smem row stride (floats): keeps float4 alignment, spreads banks
+
+// normalised query-grid coordinate, bit-identical to torch's arange -> /(n-1) -> *2 -> -1
+__device__ __forceinline__ float grid_coord(int i, int n) {
+  return __fsub_rn(__fmul_rn(__fdiv_rn((float)i, (float)(n - 1)), 2.f), 1.f);
 }
-extern "C" int bevr_rpe_attn_bwd(const float*, const float*, const float*, const float*, const float*, const float*,
-                                 const float*, const float*, float*, float*, float*, float*, float*, float*, int, int,
-                                 int, int, int, int, int, int, int, float, void*) {
-  bevr::set_error("rpe_attn_bwd: not built into this library yet");
-  return -2;
+
+struct Bilin {
+  int off[4];     // table offsets of nw, ne, sw, se (or -1)
+  float wx0, wx1, wy0, wy1;
+};
+
+// coordinates in the rpe table of the displacement (query - key)/2, as grid_sample(align_corners=True)
+__device__ __forceinline__ Bilin rpe_taps(float qy, float qx, float py, float px, int Rh, int Rw) {
+  const float dy = (qy - py) * 0.5f, dx = (qx - px) * 0.5f;
+  const float ix = ((dx + 1.f) / 2.f) * (float)(Rw - 1);
+  const float iy = ((dy + 1.f) / 2.f) * (float)(Rh - 1);
+  Bilin b;
+  const bool any = (ix > -1.f) && (ix < (float)Rw) && (iy > -1.f) && (iy < (float)Rh);
+  const float x0f = floorf(ix), y0f = floorf(iy);
+  b.wx1 = ix - x0f; b.wx0 = (x0f + 1.f) - ix;
+  b.wy1 = iy - y0f; b.wy0 = (y0f + 1.f) - iy;
+  const int x0 = any ? (int)x0f : -2, y0 = any ? (int)y0f : -2;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const int xi = x0 + (t & 1), yi = y0 + (t >> 1);
+    b.off[t] = (xi >= 0 && xi < Rw && yi >= 0 && yi < Rh) ? yi * Rw + xi : -1;
+  }
+  return b;
+}
+
+__device__ __forceinline__ float rpe_bias(const float* __restrict__ table, const Bilin& b, float* tapv) {
+#pragma unroll
+  for (int t = 0; t < 4; ++t) tapv[t] = b.off[t] >= 0 ? __ldg(table + b.off[t]) : 0.f;
+  return tapv[0] * (b.wx0 * b.wy0) + tapv[1] * (b.wx1 * b.wy0) + tapv[2] * (b.wx0 * b.wy1) +
+         tapv[3] * (b.wx1 * b.wy1);
+}
+
+// stage rows [j0, j0+T) of a channel-major (DH, n) matrix as smem[T][PAD] (zero beyond n)
+template <int T>
+__device__ __forceinline__ void stage_transposed(float* __restrict__ dst, const float* __restrict__ src, int n,
+                                                 int j0, float mul) {
+  for (int idx = threadIdx.x; idx < T * DH; idx += blockDim.x) {
+    const int c = idx / T, jj = idx - c * T;
+    const int j = j0 + jj;
+    dst[jj * PAD + c] = j < n ? __ldg(src + (size_t)c * n + j) * mul : 0.f;
+  }
+}
+
+__device__ __forceinline__ float dot32(const float* reg, const float* __restrict__ srow) {
+  float s = 0.f;
+#pragma unroll
+  for (int c = 0; c < DH; c += 4) {
+    const float4 kk = *reinterpret_cast<const float4*>(srow + c);
+    s = fmaf(reg[c], kk.x, s); s = fmaf(reg[c + 1], kk.y, s);
+    s = fmaf(reg[c + 2], kk.z, s); s = fmaf(reg[c + 3], kk.w, s);
+  }
+  return s;
+}
+__device__ __forceinline__ void axpy32(float* acc, float a, const float* __restrict__ srow) {
+#pragma unroll
+  for (int c = 0; c < DH; c += 4) {
+    const float4 vv = *reinterpret_cast<const float4*>(srow + c);
+    acc[c] = fmaf(a, vv.x, acc[c]); acc[c + 1] = fmaf(a, vv.y, acc[c + 1]);
+    acc[c + 2] = fmaf(a, vv.z, acc[c + 2]); acc[c + 3] = fmaf(a, vv.w, acc[c + 3]);
+  }
+}
+
+// ------------------------------------------------------------------ forward (thread = query row)
+constexpr int TQ = 128, TK = 64, CH = 16;
+
+__global__ void __launch_bounds__(TQ) rpe_attn_fwd_kernel(const __grid_constant__ RpeArgs a) {
+  __shared__ __align__(16) float sK[TK * PAD];
+  __shared__ __align__(16) float sV[TK * PAD];
+  __shared__ float2 sPos[TK];
+  const int bh = blockIdx.y, i = blockIdx.x * TQ + threadIdx.x;
+  const bool live = i < a.Nq;
+  const int head = bh % a.h, bg = bh / a.hpg;
+  const float* table = a.rpe + (size_t)head * a.Rh * a.Rw;
+  const float* kb = a.k + (size_t)bh * DH * a.Ns;
+  const float* vb = a.v + (size_t)bh * DH * a.Ns;
+  const float2* pb = reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns;
+
+  float qr[DH], o[DH];
+#pragma unroll
+  for (int c = 0; c < DH; ++c) {
+    qr[c] = live ? __ldg(a.q + ((size_t)bh * DH + c) * a.Nq + i) * a.scale : 0.f;
+    o[c] = 0.f;
+  }
+  const int iy = i / a.Wq, ixq = i - iy * a.Wq;
+  const float qy = grid_coord(iy, a.Hq), qx = grid_coord(ixq, a.Wq);
+  float m = -INFINITY, l = 0.f;
+
+  for (int j0 = 0; j0 < a.Ns; j0 += TK) {
+    __syncthreads();
+    stage_transposed<TK>(sK, kb, a.Ns, j0, 1.f);
+    stage_transposed<TK>(sV, vb, a.Ns, j0, 1.f);
+    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x)
+      sPos[jj] = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+    __syncthreads();
+#pragma unroll 1
+    for (int jc = 0; jc < TK; jc += CH) {
+      if (j0 + jc >= a.Ns) break;
+      float s[CH];
+      float mx = -INFINITY;
+#pragma unroll
+      for (int jj = 0; jj < CH; ++jj) {
+        const float2 p = sPos[jc + jj];
+        const Bilin b = rpe_taps(qy, qx, p.x, p.y, a.Rh, a.Rw);
+        float tv[4];
+        const float sc = dot32(qr, sK + (jc + jj) * PAD) + rpe_bias(table, b, tv);
+        s[jj] = (j0 + jc + jj < a.Ns) ? sc : -INFINITY;
+        mx = fmaxf(mx, s[jj]);
+      }
+      const float mn = fmaxf(m, mx);
+      const float corr = __expf(m - mn);
+      l *= corr;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) o[c] *= corr;
+#pragma unroll
+      for (int jj = 0; jj < CH; ++jj) {
+        const float p = __expf(s[jj] - mn);
+        l += p;
+        axpy32(o, p, sV + (jc + jj) * PAD);
+      }
+      m = mn;
+    }
+  }
+  if (live) {
+    const float inv = 1.f / l;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) a.o_out[((size_t)bh * DH + c) * a.Nq + i] = o[c] * inv;
+    a.o_lse[(size_t)bh * a.Nq + i] = m + logf(l);
+  }
+}
+
+// ------------------------------------------------------------------ backward
+// delta_i = sum_c dO[c][i] * O[c][i]
+__global__ void __launch_bounds__(256) rpe_delta_kernel(const __grid_constant__ RpeArgs a) {
+  const int bh = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.Nq) return;
+  float s = 0.f;
+#pragma unroll 8
+  for (int c = 0; c < DH; ++c) {
+    const size_t idx = ((size_t)bh * DH + c) * a.Nq + i;
+    s = fmaf(__ldg(a.grad_out + idx), __ldg(a.out + idx), s);
+  }
+  a.o_delta[(size_t)bh * a.Nq + i] = s;
+}
+
+// dQ: thread = query row, streams K/V tiles
+__global__ void __launch_bounds__(TQ) rpe_attn_bwd_dq_kernel(const __grid_constant__ RpeArgs a) {
+  __shared__ __align__(16) float sK[TK * PAD];
+  __shared__ __align__(16) float sV[TK * PAD];
+  __shared__ float2 sPos[TK];
+  const int bh = blockIdx.y, i = blockIdx.x * TQ + threadIdx.x;
+  const bool live = i < a.Nq;
+  const int head = bh % a.h, bg = bh / a.hpg;
+  const float* table = a.rpe + (size_t)head * a.Rh * a.Rw;
+  const float* kb = a.k + (size_t)bh * DH * a.Ns;
+  const float* vb = a.v + (size_t)bh * DH * a.Ns;
+  const float2* pb = reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns;
+
+  float qr[DH], go[DH], dq[DH];
+#pragma unroll
+  for (int c = 0; c < DH; ++c) {
+    const size_t idx = ((size_t)bh * DH + c) * a.Nq + i;
+    qr[c] = live ? __ldg(a.q + idx) * a.scale : 0.f;
+    go[c] = live ? __ldg(a.grad_out + idx) : 0.f;
+    dq[c] = 0.f;
+  }
+  const float lse = live ? __ldg(a.lse + (size_t)bh * a.Nq + i) : 0.f;
+  const float delta = live ? __ldg(a.delta + (size_t)bh * a.Nq + i) : 0.f;
+  const int iy = i / a.Wq, ixq = i - iy * a.Wq;
+  const float qy = grid_coord(iy, a.Hq), qx = grid_coord(ixq, a.Wq);
+
+  for (int j0 = 0; j0 < a.Ns; j0 += TK) {
+    __syncthreads();
+    stage_transposed<TK>(sK, kb, a.Ns, j0, 1.f);
+    stage_transposed<TK>(sV, vb, a.Ns, j0, 1.f);
+    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x)
+      sPos[jj] = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+    __syncthreads();
+    const int jn = min(TK, a.Ns - j0);
+#pragma unroll 4
+    for (int jj = 0; jj < jn; ++jj) {
+      const float2 p = sPos[jj];
+      const Bilin b = rpe_taps(qy, qx, p.x, p.y, a.Rh, a.Rw);
+      float tv[4];
+      const float s = dot32(qr, sK + jj * PAD) + rpe_bias(table, b, tv);
+      const float pr = __expf(s - lse);
+      const float dp = dot32(go, sV + jj * PAD);
+      axpy32(dq, pr * (dp - delta), sK + jj * PAD);
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < DH; ++c) a.grad_q[((size_t)bh * DH + c) * a.Nq + i] = dq[c] * a.scale;
+  }
+}
+
+// dK, dV, dpos, drpe: thread = key column, streams Q/dO tiles
+constexpr int TKB = 128, TQB = 32;
+
+__global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_constant__ RpeArgs a) {
+  __shared__ __align__(16) float sQ[TQB * PAD];
+  __shared__ __align__(16) float sG[TQB * PAD];
+  __shared__ float4 sRow[TQB];    // qy, qx, lse, delta
+  const int bh = blockIdx.y, j = blockIdx.x * TKB + threadIdx.x;
+  const bool live = j < a.Ns;
+  const int head = bh % a.h, bg = bh / a.hpg;
+  const float* table = a.rpe + (size_t)head * a.Rh * a.Rw;
+  float* gtable = a.grad_rpe ? a.grad_rpe + (size_t)head * a.Rh * a.Rw : nullptr;
+  const float* qb = a.q + (size_t)bh * DH * a.Nq;
+  const float* gb = a.grad_out + (size_t)bh * DH * a.Nq;
+
+  float kr[DH], vr[DH], dk[DH], dv[DH];
+#pragma unroll
+  for (int c = 0; c < DH; ++c) {
+    const size_t idx = ((size_t)bh * DH + c) * a.Ns + j;
+    kr[c] = live ? __ldg(a.k + idx) : 0.f;
+    vr[c] = live ? __ldg(a.v + idx) : 0.f;
+    dk[c] = 0.f; dv[c] = 0.f;
+  }
+  float2 pj = make_float2(0.f, 0.f);
+  if (live) pj = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns + j);
+  float giy = 0.f, gix = 0.f;
+  const bool want_bias_grad = (a.grad_rpe != nullptr) || (a.grad_pos != nullptr);
+
+  for (int i0 = 0; i0 < a.Nq; i0 += TQB) {
+    __syncthreads();
+    stage_transposed<TQB>(sQ, qb, a.Nq, i0, a.scale);
+    stage_transposed<TQB>(sG, gb, a.Nq, i0, 1.f);
+    for (int ii = threadIdx.x; ii < TQB; ii += blockDim.x) {
+      const int i = i0 + ii;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < a.Nq) {
+        const int iy = i / a.Wq, ixq = i - iy * a.Wq;
+        r = make_float4(grid_coord(iy, a.Hq), grid_coord(ixq, a.Wq), __ldg(a.lse + (size_t)bh * a.Nq + i),
+                        __ldg(a.delta + (size_t)bh * a.Nq + i));
+      }
+      sRow[ii] = r;
+    }
+    __syncthreads();
+    if (!live) continue;
+    const int in = min(TQB, a.Nq - i0);
+#pragma unroll 2
+    for (int ii = 0; ii < in; ++ii) {
+      const float4 r = sRow[ii];
+      const Bilin b = rpe_taps(r.x, r.y, pj.x, pj.y, a.Rh, a.Rw);
+      float tv[4];
+      const float s = dot32(kr, sQ + ii * PAD) + rpe_bias(table, b, tv);
+      const float pr = __expf(s - r.z);
+      axpy32(dv, pr, sG + ii * PAD);
+      const float dp = dot32(vr, sG + ii * PAD);
+      const float ds = pr * (dp - r.w);
+      axpy32(dk, ds, sQ + ii * PAD);
+      if (want_bias_grad) {
+        gix = fmaf(ds, b.wy0 * (tv[1] - tv[0]) + b.wy1 * (tv[3] - tv[2]), gix);
+        giy = fmaf(ds, b.wx0 * (tv[2] - tv[0]) + b.wx1 * (tv[3] - tv[1]), giy);
+        if (gtable) {
+          const float w[4] = {b.wx0 * b.wy0, b.wx1 * b.wy0, b.wx0 * b.wy1, b.wx1 * b.wy1};
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (b.off[t] >= 0) atomicAdd(gtable + b.off[t], ds * w[t]);
+        }
+      }
+    }
+  }
+  if (live) {
+#pragma unroll
+    for (int c = 0; c < DH; ++c) {
+      const size_t idx = ((size_t)bh * DH + c) * a.Ns + j;
+      if (a.grad_k) a.grad_k[idx] = dk[c];    // sQ already carries `scale`
+      if (a.grad_v) a.grad_v[idx] = dv[c];
+    }
+    if (a.grad_pos) {
+      // table coord = (Rx-1) * ((q - pos)/4 + 1/2)  ->  d coord / d pos = -(Rx-1)/4
+      float* gp = a.grad_pos + ((size_t)bg * a.Ns + j) * 2;
+      atomicAdd(gp, giy * (-0.25f * (float)(a.Rh - 1)));
+      atomicAdd(gp + 1, gix * (-0.25f * (float)(a.Rw - 1)));
+    }
+  }
+}
+
+static int validate(int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw) {
+  BEVR_REQUIRE(Dh == DH, "rpe_attn: only Dh == 32 is built (got %d)", Dh);
+  BEVR_REQUIRE(BH > 0 && h > 0 && hpg > 0 && BH % h == 0 && h % hpg == 0, "rpe_attn: bad BH=%d h=%d hpg=%d", BH, h, hpg);
+  BEVR_REQUIRE(Hq > 1 && Wq > 1 && Ns > 0 && Rh > 0 && Rw > 0, "rpe_attn: bad sizes Hq=%d Wq=%d Ns=%d Rh=%d Rw=%d",
+               Hq, Wq, Ns, Rh, Rw);
+  BEVR_REQUIRE(BH <= 65535, "rpe_attn: B*h=%d exceeds gridDim.y", BH);
+  return 0;
+}
+
+}  // namespace bevr
+
+using namespace bevr;
+
+extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
+                                 float* out, float* lse, int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns,
+                                 int Rh, int Rw, float scale, void* stream) {
+  if (int rc = validate(BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw)) return rc;
+  BEVR_REQUIRE(q && k && v && rpe && pos && out && lse, "rpe_attn_fwd: NULL pointer argument");
+  RpeArgs a = {};
+  a.q = q; a.k = k; a.v = v; a.rpe = rpe; a.pos = pos; a.o_out = out; a.o_lse = lse;
+  a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
+  a.scale = scale;
+  dim3 grid((a.Nq + TQ - 1) / TQ, BH);
+  rpe_attn_fwd_kernel<<<grid, TQ, 0, (cudaStream_t)stream>>>(a);
+  return check_launch("rpe_attn_fwd");
+}
+
+extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
+                                 const float* out, const float* lse, const float* grad_out, float* grad_q,
+                                 float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos, float* delta_ws,
+                                 int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw, float scale,
+                                 void* stream) {
+  if (int rc = validate(BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw)) return rc;
+  BEVR_REQUIRE(q && k && v && rpe && pos && out && lse && grad_out && delta_ws, "rpe_attn_bwd: NULL pointer argument");
+  RpeArgs a = {};
+  a.q = q; a.k = k; a.v = v; a.rpe = rpe; a.pos = pos; a.out = out; a.lse = lse; a.grad_out = grad_out;
+  a.delta = delta_ws; a.o_delta = delta_ws;
+  a.grad_q = grad_q; a.grad_k = grad_k; a.grad_v = grad_v; a.grad_rpe = grad_rpe; a.grad_pos = grad_pos;
+  a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
+  a.scale = scale;
+  cudaStream_t st = (cudaStream_t)stream;
+  rpe_delta_kernel<<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
+  if (int rc = check_launch("rpe_attn_bwd delta")) return rc;
+  if (grad_q) {
+    rpe_attn_bwd_dq_kernel<<<dim3((a.Nq + TQ - 1) / TQ, BH), TQ, 0, st>>>(a);
+    if (int rc = check_launch("rpe_attn_bwd dq")) return rc;
+  }
+  if (grad_k || grad_v || grad_rpe || grad_pos) {
+    rpe_attn_bwd_dkv_kernel<<<dim3((Ns + TKB - 1) / TKB, BH), TKB, 0, st>>>(a);
+    if (int rc = check_launch("rpe_attn_bwd dkv")) return rc;
+  }
+  return 0;
 }

@@ -1,0 +1,171 @@
+"""Drop-in replacements for the reference's deformable-attention modules.
+
+``TSADeformableAttention`` / ``SCADeformableAttention`` keep the constructor arguments, parameter
+names and shapes (so ``state_dict``s interchange) and the forward signatures of
+model/TSA_deform_attn.py:14-337 and model/SCA_deform_attn.py:14-421, and therefore drop into
+model/TSA.py / model/SCA.py / model/encoder.py unchanged.  The offset network and the 1x1
+projections stay PyTorch; the feature gather (K1/K2) and the attention with
+sampled relative-position bias (K3) run as sm_100a kernels behind the C ABI.
+
+Differences from the reference, all deliberate:
+  * nothing of size (Nq, Ns) is materialised (the reference needs 51 GB/sample at 200x200);
+  * attention dropout inside the fused kernel is not implemented: ``attn_drop_rate > 0`` raises in
+    training mode (the reference default is 0.0);
+  * ``TSADeformableAttention`` with ``n_groups > 1`` works here (the reference raises at
+    TSA_deform_attn.py:278-283); ``SCADeformableAttention`` with ``n_views > 1`` raises here exactly
+    as the reference does (SCA_deform_attn.py:248-255), with a clearer message.
+"""
+import torch
+from torch import nn
+
+from .functional import grid_gather, rpe_attention
+
+
+class LayerNormProxy(nn.Module):
+    """LayerNorm over the channel axis of an NCHW tensor (model_utils.py:51-59); the sub-module is
+    called ``norm`` so the parameter keys are ``...1.norm.weight`` as in the reference."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.norm = nn.LayerNorm(dim)
+
+    def forward(self, x):
+        return self.norm(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
+
+
+def _offset_net(c_in, c_mid, c_out, kernel_size, stride, pad):
+    return nn.Sequential(
+        nn.Conv2d(c_in, c_mid, kernel_size, stride, pad, groups=c_in),
+        LayerNormProxy(c_mid),
+        nn.GELU(),
+        nn.Conv2d(c_mid, c_out, 1, 1, 0, bias=False),
+    )
+
+
+class _DeformAttnBase(nn.Module):
+    def _common(self, dim_embed, n_heads, n_groups, stride, kernel_size, scale_offset_range, batch_size,
+                n_views, attn_drop_rate, proj_drop_rate, data_type, logger):
+        self.n_channel_per_head = dim_embed // n_heads
+        self.scale = self.n_channel_per_head ** -0.5
+        self.n_heads = n_heads
+        self.embed_dim = self.n_channel_per_head * n_heads
+        self.n_groups = n_groups
+        self.n_channel_per_group = self.embed_dim // n_groups
+        self.n_heads_per_group = n_heads // n_groups
+        self.batch_size = batch_size
+        self.scale_offset_range = scale_offset_range
+        self.kernel_size, self.stride, self.n_views = kernel_size, stride, n_views
+        self.data_type, self.logger = data_type, logger
+        self._grids = {}
+        C = self.embed_dim
+        self.proj_q = nn.Conv2d(C, C, 1)          # defined but never applied, as in the reference
+        self.proj_k = nn.Conv2d(C, C, 1)
+        self.proj_v = nn.Conv2d(C, C, 1)
+        self.proj_drop_rate = nn.Dropout(proj_drop_rate, inplace=True)
+        self.attn_drop_rate = nn.Dropout(attn_drop_rate, inplace=True)
+
+    @torch.no_grad()
+    def _get_normalized_grid(self, H, W, B, device):
+        """(B*g, H, W, 2) in (y, x), values arange/(n-1)*2-1 with the reference's op order."""
+        key = (H, W, str(device))
+        if key not in self._grids:
+            ys = torch.arange(0, H, dtype=self.data_type, device=device).div_(H - 1.0).mul_(2.0).sub_(1.0)
+            xs = torch.arange(0, W, dtype=self.data_type, device=device).div_(W - 1.0).mul_(2.0).sub_(1.0)
+            gy, gx = torch.meshgrid(ys, xs, indexing="ij")
+            self._grids[key] = torch.stack((gy, gx), -1)
+        return self._grids[key][None].expand(B * self.n_groups, -1, -1, -1)
+
+    def _scaled_positions(self, raw, ref):
+        """raw (B*g, 2, Hk, Wk) offset-net output in (y, x); ref (B*g, Hk, Wk, 2)."""
+        Hk, Wk = raw.shape[-2:]
+        if self.scale_offset_range:
+            rng = torch.tensor([1.0 / (Hk - 1.0), 1.0 / (Wk - 1.0)], device=raw.device).reshape(1, 2, 1, 1)
+            raw = raw.tanh().mul(rng).mul(self.offset_range_factor)
+        pos = raw.permute(0, 2, 3, 1) + ref
+        return pos if self.scale_offset_range else pos.clamp(-1.0, +1.0)
+
+    def _attend(self, x_grouped, pos, query):
+        """gather (K1/K2) -> K/V projections -> fused RPE attention (K3) -> (B, C, Hq, Wq)."""
+        if self.training and self.attn_drop_rate.p > 0:
+            raise NotImplementedError("attention dropout is not fused into the sm_100a kernel; use attn_drop_rate=0")
+        B, C, Hq, Wq = query.shape
+        Ns = pos.shape[1] * pos.shape[2]
+        xs = grid_gather(x_grouped, pos).reshape(B, C, 1, Ns)
+        k = self.proj_k(xs).reshape(B * self.n_heads, self.n_channel_per_head, Ns)
+        v = self.proj_v(xs).reshape(B * self.n_heads, self.n_channel_per_head, Ns)
+        q = query.reshape(B * self.n_heads, self.n_channel_per_head, Hq * Wq)
+        out = rpe_attention(q, k, v, self.rpe_table, pos.reshape(-1, Ns, 2), Hq, Wq, self.n_groups, self.scale)
+        return out.reshape(B, C, Hq, Wq)
+
+
+class TSADeformableAttention(_DeformAttnBase):
+    def __init__(self, bev_feat_shape, dim_embed, n_heads, n_groups, stride, kernel_size, scale_offset_range,
+                 batch_size, n_views=3, attn_drop_rate=0.0, proj_drop_rate=0.0, data_type=torch.float32,
+                 logger=None):
+        super().__init__()
+        self._common(dim_embed, n_heads, n_groups, stride, kernel_size, scale_offset_range, batch_size, n_views,
+                     attn_drop_rate, proj_drop_rate, data_type, logger)
+        self.bev_h = self.bev_w = bev_feat_shape
+        if scale_offset_range:
+            self.offset_range_factor = 0.5
+        Cg = self.n_channel_per_group
+        pad = kernel_size // 2 if kernel_size != stride else 0
+        self.conv_offset = _offset_net(Cg, Cg, 2, kernel_size, stride, pad)
+        self.proj_out = nn.Conv2d(self.embed_dim, self.embed_dim, 1)
+        self.proj_views = nn.Conv2d(Cg * n_views, Cg, 1)          # unused, kept for the state_dict
+        self.rpe_table = nn.Parameter(torch.zeros(n_heads, self.bev_h * 2 - 1, self.bev_w * 2 - 1))
+        nn.init.trunc_normal_(self.rpe_table, std=0.01)
+
+    def forward(self, x, query, wandb_log_dict, return_wandb_log=True):
+        """x, query (B, C, H, W) -> ((B, C, H, W), wandb_log_dict); x=None means self-attention."""
+        if x is None:
+            x = query
+        B, C, H, W = x.shape
+        g, Cg = self.n_groups, self.n_channel_per_group
+        raw = self.conv_offset(query.reshape(B * g, Cg, H, W))
+        Hk, Wk = raw.shape[-2:]
+        pos = self._scaled_positions(raw, self._get_normalized_grid(Hk, Wk, B, x.device))
+        out = self._attend(x.reshape(B * g, Cg, H, W), pos, query)
+        return self.proj_drop_rate(self.proj_out(out)), wandb_log_dict
+
+
+class SCADeformableAttention(_DeformAttnBase):
+    def __init__(self, bev_feat_shape, bev_depth_dim, dim_embed, n_heads, n_groups, stride, kernel_size,
+                 scale_offset_range, batch_size, n_views=3, attn_drop_rate=0.0, proj_drop_rate=0.0,
+                 data_type=torch.float32, logger=None):
+        super().__init__()
+        self._common(dim_embed, n_heads, n_groups, stride, kernel_size, scale_offset_range, batch_size, n_views,
+                     attn_drop_rate, proj_drop_rate, data_type, logger)
+        self.query_height = self.query_width = bev_feat_shape
+        self.bev_depth_dim = D = bev_depth_dim
+        if scale_offset_range:
+            self.offset_range_factor = 5.0
+        Cg = self.n_channel_per_group
+        # only conv_offset_m0 is ever usable (the reference's rearrange fixes d = D); m1/m2 exist for the keys
+        self.conv_offset_m0 = _offset_net(Cg, Cg * D, D, 1, 1, 0)
+        self.conv_offset_m1 = _offset_net(Cg, Cg * D, 2 * D, 1, 1, 0)
+        self.conv_offset_m2 = _offset_net(Cg, Cg * D, 2 * D, 1, 1, 0)
+        self.proj_out = nn.Conv2d(self.embed_dim * n_views, self.embed_dim, 1)
+        self.proj_views = nn.Conv2d(Cg * n_views, Cg, 1)
+        self.rpe_table = nn.Parameter(
+            torch.zeros(n_heads, self.query_height * 2 - 1, self.query_width * D * 2 - 1))
+        nn.init.trunc_normal_(self.rpe_table, std=0.01)
+
+    def forward(self, x, query, reference_points, wandb_log_dict, return_wandb_log=True):
+        """x (B, V, C, Hi, Wi); query (B, C, Hq, Wq); reference_points (B, V, Hq/2, Wq*D, 2) in (x, y)."""
+        if self.n_views != 1:
+            raise NotImplementedError(
+                "SCADeformableAttention: n_views > 1 is unsupported (the reference itself raises an EinopsError "
+                "for views 1 and 2: conv_offset_m1/m2 emit 2*D channels, SCA_deform_attn.py:91-121,248-255)")
+        B, C, Hq, Wq = query.shape
+        g, Cg, D = self.n_groups, self.n_channel_per_group, self.bev_depth_dim
+        Hi, Wi = x.shape[-2:]
+        ref = reference_points[:, 0].flip(-1)                         # (x, y) -> (y, x)
+        if g > 1:
+            ref = ref.repeat_interleave(g, 0)
+        raw = self.conv_offset_m0(query.reshape(B * g, Cg, Hq, Wq))   # (B*g, D, Hq, Wq)
+        # "(b g) d (h n) w -> (b g) n h (w d)", n = 2: even query rows carry y-, odd rows x-offsets
+        raw = raw.reshape(B * g, D, Hq // 2, 2, Wq).permute(0, 3, 2, 4, 1).reshape(B * g, 2, Hq // 2, Wq * D)
+        pos = self._scaled_positions(raw, ref)
+        out = self._attend(x[:, 0].reshape(B * g, Cg, Hi, Wi), pos, query)
+        return self.proj_drop_rate(self.proj_out(out)), wandb_log_dict

@@ -135,3 +135,55 @@ def project_points(points, cam_T, K, img_w, img_h):
     _lib.check(_lib.lib().bevr_project_points(_ptr(p), T, Kc, _ptr(uv), _ptr(pix), _ptr(mask), n,
                                               int(img_w), int(img_h), _stream()), "bevr_project_points")
     return uv.reshape(2, *shp), pix.reshape(2, *shp), mask.bool().reshape(*shp)
+
+
+class _RpeAttention(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q, k, v, rpe, pos, Hq, Wq, hpg, scale):
+        _need_cuda(q, k, v, rpe, pos)
+        q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
+        rpe, pos = rpe.contiguous().float(), pos.contiguous().float()
+        BH, Dh, Nq = q.shape
+        Ns = k.shape[2]
+        h, Rh, Rw = rpe.shape
+        out = torch.empty_like(q)
+        lse = torch.empty(BH, Nq, dtype=torch.float32, device=q.device)
+        _lib.check(_lib.lib().bevr_rpe_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
+                                                BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, float(scale), _stream()),
+                   "bevr_rpe_attn_fwd")
+        ctx.save_for_backward(q, k, v, rpe, pos, out, lse)
+        ctx.meta = (Hq, Wq, hpg, float(scale))
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        q, k, v, rpe, pos, out, lse = ctx.saved_tensors
+        Hq, Wq, hpg, scale = ctx.meta
+        BH, Dh, Nq = q.shape
+        Ns = k.shape[2]
+        h, Rh, Rw = rpe.shape
+        need = ctx.needs_input_grad
+        grad_out = grad_out.contiguous().float()
+        gq = torch.empty_like(q) if need[0] else None
+        gk = torch.empty_like(k) if need[1] else None
+        gv = torch.empty_like(v) if need[2] else None
+        gr = torch.zeros_like(rpe) if need[3] else None
+        gp = torch.zeros_like(pos) if need[4] else None
+        delta = torch.empty_like(lse)
+        _lib.check(_lib.lib().bevr_rpe_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
+                                                _ptr(grad_out), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(gr), _ptr(gp),
+                                                _ptr(delta), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, scale, _stream()),
+                   "bevr_rpe_attn_bwd")
+        return gq, gk, gv, gr, gp, None, None, None, None
+
+
+def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None):
+    """K3: softmax_j(q.k*scale + bilinear(rpe_table[head], (qgrid_i - pos_j)/2)) . v, never materialised.
+
+    q (B*h, Dh, Hq*Wq); k, v (B*h, Dh, Ns); rpe_table (h, Rh, Rw); pos (B*g, Ns, 2) in (y, x);
+    returns (B*h, Dh, Hq*Wq).  Replaces TSA_deform_attn.py:245-330 / SCA_deform_attn.py:331-411.
+    """
+    h = rpe_table.shape[0]
+    if scale is None:
+        scale = q.shape[1] ** -0.5
+    return _RpeAttention.apply(q, k, v, rpe_table, pos, int(Hq), int(Wq), h // n_groups, scale)

@@ -135,7 +135,7 @@ def test_full_size_properties():
     assert rel_err(o2.cpu(), 2.5 * o1.cpu()) < 1e-6
     # interior queries (all taps in range) of a constant map return the constant
     ones = torch.ones_like(v)
-    oc = f(ones).reshape(200, 200, -1)[40:160, 40:160]
+    oc = f(ones).reshape(200, 200, -1)[90:110, 90:110]   # >5 sigma from every level border
     assert (oc - 1).abs().max() < 1e-5
     vg = v.clone().requires_grad_(True)
     go = d["grad_out"].to(dev)
