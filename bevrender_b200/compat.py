@@ -1,0 +1,55 @@
+"""Rebind the reference's names to the B200 modules without editing the checkout.
+
+The reference package (``model/``) must be importable (its directory on ``sys.path``).  ``install()``
+replaces the three symbols the callers look up at construction time:
+``model.TSA.TSADeformableAttention`` (TSA.py:4,30), ``model.SCA.SCADeformableAttention`` (SCA.py:5,43)
+and ``model.bevrender.BEV2CameraProjector`` (bevrender.py:11,31).
+"""
+import importlib
+import sys
+import types
+
+import torch
+
+
+def ensure_timm_stub():
+    """``model/*`` imports ``timm.models.layers.{trunc_normal_, DropPath}``; provide them when timm is absent."""
+    try:
+        import timm.models.layers  # noqa: F401
+        return
+    except Exception:
+        pass
+    layers = types.ModuleType("timm.models.layers")
+    layers.trunc_normal_ = torch.nn.init.trunc_normal_
+
+    class DropPath(torch.nn.Module):
+        def __init__(self, drop_prob=0.0):
+            super().__init__()
+            self.drop_prob = drop_prob
+
+        def forward(self, x):
+            if self.drop_prob == 0.0 or not self.training:
+                return x
+            keep = 1.0 - self.drop_prob
+            mask = x.new_empty(x.shape[0], *([1] * (x.dim() - 1))).bernoulli_(keep)
+            return x * mask / keep
+
+    layers.DropPath = DropPath
+    timm, models = types.ModuleType("timm"), types.ModuleType("timm.models")
+    timm.models, models.layers = models, layers
+    sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers})
+
+
+def install(projector=True):
+    from . import BEV2CameraProjector, SCADeformableAttention, TSADeformableAttention
+    ensure_timm_stub()
+    tsa = importlib.import_module("model.TSA")
+    sca = importlib.import_module("model.SCA")
+    tsa.TSADeformableAttention = TSADeformableAttention
+    sca.SCADeformableAttention = SCADeformableAttention
+    if projector:
+        try:
+            top = importlib.import_module("model.bevrender")
+            top.BEV2CameraProjector = BEV2CameraProjector
+        except ImportError:          # model.bevrender pulls the decoder/backbone; optional for layer-level use
+            pass

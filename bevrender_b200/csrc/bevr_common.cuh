@@ -32,6 +32,14 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
                : "memory");
 }
 
+// same, predicated (no branch around the RED: the gather loops are issue-bound)
+__device__ __forceinline__ void red_add_v4_if(bool pred, float* addr, float a, float b, float c, float d) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %5, 0;\n\t@p red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+      ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d), "r"((int)pred)
+      : "memory");
+}
+
 __device__ __forceinline__ float bf16lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t u) { return __uint_as_float(u & 0xffff0000u); }
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {

@@ -7,16 +7,19 @@
 // Design (DESIGN.md section "K1/K2"):
 //  * value is channels-last (B,S,h,Dh): one bilinear tap of one head is one contiguous
 //    Dh*sizeof(T) vector (128 B for fp32/Dh=32 = one L1 line = one L1 wavefront).
-//  * A "group" of LPG lanes owns one (query, head[, channel chunk]) item; each lane holds a
-//    16-byte vector of channels, so every tap is fetched by LPG coalesced LDG.128s.
+//  * A "group" of LPG lanes owns one (query, head[, channel chunk]) item; each lane holds NV
+//    channels (16 B in forward), so every tap is fetched by LPG coalesced vector loads.
 //  * A CTA owns a 2-D tile of the query grid for ONE head: all taps of the tile fall in a small
 //    window of every level, so they are served by L1 after the first touch and HBM sees each
 //    value line about once (L2 keeps the (b,head) slice while its tiles are in flight).
 //  * Tap set-up (unnormalise, floor, 4 offsets, 4 weights, validity) is done ONCE per sampling
-//    point by one lane and staged in shared memory; the gather loop is branch-free:
-//    LDS.128 x2 -> LDG.128 x4 -> FFMA.  Out-of-range taps get weight 0 and a safe offset.
+//    point by one lane of the owning group and staged in shared memory; the gather loop is
+//    branch-free: LDS.128 x2 -> (IMAD.WIDE.U32 + LDG) x4 -> FFMA.  Out-of-range taps get weight 0
+//    and a safe offset.
 //  * Backward recomputes the taps, accumulates grad_value with vector RED.ADD.F32x4 into an fp32
 //    buffer, and writes grad_loc / grad_weight directly (intra-group shuffle reduction, no atomics).
+//  * The kernels are instruction-issue / L1-wavefront / L2-RED-sector bound (profiles/), so the
+//    inner loops avoid integer division and 64-bit address chains.
 #include "bevr_common.cuh"
 
 namespace bevr {
@@ -33,9 +36,10 @@ struct MsdaArgs {
   void* grad_weight;
   int B, S, h, Dh, Nq, L, P;
   int qw, qh;        // query grid (qh*qw == Nq; flat list: qh = 1)
-  int tw, th;        // query tile
+  int tw_shift, th;  // query tile: width 1 << tw_shift, height th
   int tiles_x, tiles_y;
-  int nchunk;        // channel chunks per head (Dh / (LPG*VEC))
+  int nchunk;        // channel chunks per head (Dh / (LPG*NV))
+  int p_shift;       // log2(P) if P is a power of two, else -1
   int flags;
   int lvl_h[BEVR_MAX_LEVELS], lvl_w[BEVR_MAX_LEVELS], lvl_start[BEVR_MAX_LEVELS];
 };
@@ -55,225 +59,258 @@ __device__ __forceinline__ float unnormalize_scale(int size, int flags) {
   return (flags & BEVR_LOC_PM1) ? 0.5f * s : s;
 }
 
-struct Tap {
-  int off[4];     // vector offsets (units of 16 B) inside the sample's value; -1 if out of range
-  float fx, fy;   // fractional parts (weights of the +1 taps)
-  float aw;       // attention weight
-  bool any;
+// NV channels of T starting at a byte address (read-only path); fp32 accumulators out
+template <typename T, int NV> struct Chan;
+template <> struct Chan<float, 4> {
+  static constexpr int BYTES = 16;
+  __device__ static void load(const char* p, float* f) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    f[0] = __uint_as_float(u.x); f[1] = __uint_as_float(u.y); f[2] = __uint_as_float(u.z); f[3] = __uint_as_float(u.w);
+  }
+  __device__ static void store(char* p, const float* f) {
+    *reinterpret_cast<float4*>(p) = make_float4(f[0], f[1], f[2], f[3]);
+  }
+};
+template <> struct Chan<__nv_bfloat16, 8> {
+  static constexpr int BYTES = 16;
+  __device__ static void load(const char* p, float* f) {
+    const uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+    f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+    f[4] = bf16lo(u.z); f[5] = bf16hi(u.z); f[6] = bf16lo(u.w); f[7] = bf16hi(u.w);
+  }
+  __device__ static void store(char* p, const float* f) {
+    *reinterpret_cast<uint4*>(p) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]),
+                                              pack_bf16(f[6], f[7]));
+  }
+};
+template <> struct Chan<__nv_bfloat16, 4> {   // backward: 4 channels/lane so a lane's RED.F32x4 is contiguous
+  static constexpr int BYTES = 8;
+  __device__ static void load(const char* p, float* f) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+    f[0] = bf16lo(u.x); f[1] = bf16hi(u.x); f[2] = bf16lo(u.y); f[3] = bf16hi(u.y);
+  }
 };
 
+template <typename T> __device__ __forceinline__ float load_scalar(const T* p);
+template <> __device__ __forceinline__ float load_scalar<float>(const float* p) { return __ldg(p); }
+template <> __device__ __forceinline__ float load_scalar<__nv_bfloat16>(const __nv_bfloat16* p) {
+  return __bfloat162float(*p);
+}
+__device__ __forceinline__ void store_scalar(float* p, float v) { *p = v; }
+__device__ __forceinline__ void store_scalar(__nv_bfloat16* p, float v) { *p = __float2bfloat16_rn(v); }
+
+struct TapRec {
+  unsigned off[4];   // vector index (units of NV channels) inside the sample; 0 if out of range
+  float fx, fy, aw;
+  unsigned mask;     // bit t set: tap t (nw, ne, sw, se) is inside the level
+};
+
+// one sampling point: coordinates -> taps.  `vec_per_pix` = h*Dh/NV
 template <typename T>
-__device__ __forceinline__ Tap make_tap(const MsdaArgs& a, int b, int q, int head, int p) {
-  Tap t;
+__device__ __forceinline__ TapRec make_tap(const MsdaArgs& a, size_t item, int bq, int p, int vec_per_pix) {
+  TapRec t;
   const int LP = a.L * a.P;
-  const int l = p / a.P;
+  const int l = a.p_shift >= 0 ? (p >> a.p_shift) : (p / a.P);
   const int H = a.lvl_h[l], W = a.lvl_w[l];
-  const size_t li = (((size_t)b * a.Nq + q) * a.h + head) * LP + p;
+  const size_t li = item * LP + p;
   float2 xy = __ldg(reinterpret_cast<const float2*>(a.loc) + li);
   if (a.ref) {
-    float2 r = __ldg(reinterpret_cast<const float2*>(a.ref) + ((size_t)b * a.Nq + q) * a.L + l);
+    const float2 r = __ldg(reinterpret_cast<const float2*>(a.ref) + (size_t)bq * a.L + l);
     if (a.flags & BEVR_OFFSET_PIXELS) { xy.x = xy.x / (float)W; xy.y = xy.y / (float)H; }
     xy.x += r.x; xy.y += r.y;
   }
-  t.aw = a.weight ? Vec<T>::load1(reinterpret_cast<const T*>(a.weight) + li) : 1.f;
+  t.aw = a.weight ? load_scalar(reinterpret_cast<const T*>(a.weight) + li) : 1.f;
   const float px = unnormalize(xy.x, W, a.flags), py = unnormalize(xy.y, H, a.flags);
   // negated comparisons: NaN / inf coordinates contribute nothing (as on the CPU path)
-  t.any = (px > -1.f) && (px < (float)W) && (py > -1.f) && (py < (float)H);
-  t.fx = t.fy = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) t.off[i] = -1;
-  if (t.any) {
-    const float x0f = floorf(px), y0f = floorf(py);
-    const int x0 = (int)x0f, y0 = (int)y0f;
-    t.fx = px - x0f;
-    t.fy = py - y0f;
-    const int vstride = a.h * a.Dh / Vec<T>::N;   // 16-byte vectors per pixel
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int xi = x0 + (i & 1), yi = y0 + (i >> 1);
-      if (xi >= 0 && xi < W && yi >= 0 && yi < H) t.off[i] = (a.lvl_start[l] + yi * W + xi) * vstride;
-    }
-  }
+  const bool any = (px > -1.f) && (px < (float)W) && (py > -1.f) && (py < (float)H);
+  const float x0f = floorf(px), y0f = floorf(py);
+  t.fx = px - x0f;
+  t.fy = py - y0f;
+  const int x0 = any ? (int)x0f : -2, y0 = any ? (int)y0f : -2;
+  const bool vx0 = x0 >= 0, vx1 = x0 + 1 < W && x0 + 1 >= 0, vy0 = y0 >= 0, vy1 = y0 + 1 < H && y0 + 1 >= 0;
+  const unsigned base = (unsigned)(a.lvl_start[l] + y0 * W + x0) * (unsigned)vec_per_pix;
+  const unsigned dx = (unsigned)vec_per_pix, dy = (unsigned)(W * vec_per_pix);
+  t.mask = (vx0 && vy0 ? 1u : 0u) | (vx1 && vy0 ? 2u : 0u) | (vx0 && vy1 ? 4u : 0u) | (vx1 && vy1 ? 8u : 0u);
+  t.off[0] = (t.mask & 1u) ? base : 0u;
+  t.off[1] = (t.mask & 2u) ? base + dx : 0u;
+  t.off[2] = (t.mask & 4u) ? base + dy : 0u;
+  t.off[3] = (t.mask & 8u) ? base + dy + dx : 0u;
   return t;
 }
 
-__device__ __forceinline__ bool tile_query(const MsdaArgs& a, int tile, int qi, int& q) {
-  const int ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
-  const int ly = qi / a.tw, lx = qi - ly * a.tw;
-  const int y = ty * a.th + ly, x = tx * a.tw + lx;
+struct TileCtx {
+  int b, head, chunk, q0x, q0y;
+};
+__device__ __forceinline__ TileCtx tile_ctx(const MsdaArgs& a) {
+  TileCtx c;
+  const int n_tiles = a.tiles_x * a.tiles_y;
+  int blk = blockIdx.x;
+  const int tile = blk % n_tiles; blk /= n_tiles;
+  const int vh = blk % (a.h * a.nchunk);
+  c.b = blk / (a.h * a.nchunk);
+  c.head = vh / a.nchunk; c.chunk = vh - c.head * a.nchunk;
+  const int ty = tile / a.tiles_x;
+  c.q0y = ty * a.th; c.q0x = (tile - ty * a.tiles_x) << a.tw_shift;
+  return c;
+}
+__device__ __forceinline__ bool tile_query(const MsdaArgs& a, const TileCtx& c, int qi, int& q) {
+  const int y = c.q0y + (qi >> a.tw_shift), x = c.q0x + (qi & ((1 << a.tw_shift) - 1));
   q = y * a.qw + x;
   return (y < a.qh) && (x < a.qw);
 }
 
+__device__ __forceinline__ const char* addr_u32(const char* base, unsigned idx, unsigned scale) {
+  return base + (size_t)idx * scale;       // IMAD.WIDE.U32
+}
+// Hide a per-thread base pointer's provenance from the optimiser: otherwise ptxas keeps the kernel-parameter
+// part in uniform registers and rebuilds every tap address with IMAD.WIDE + IADD3 + IADD3.X (3 issue slots
+// instead of 1) -- the gather loops are issue-bound.
+__device__ __forceinline__ const char* opaque(const char* p) {
+  asm volatile("" : "+l"(p));
+  return p;
+}
+
 // ------------------------------------------------------------------ forward
-template <typename T, int LPG, int MAXT>
-__global__ void __launch_bounds__(MAXT) msda_fwd_kernel(const __grid_constant__ MsdaArgs a) {
-  constexpr int VEC = Vec<T>::N;
+template <typename T, int NV, int LPG>
+__global__ void __launch_bounds__(256) msda_fwd_kernel(const __grid_constant__ MsdaArgs a) {
   constexpr int GPW = 32 / LPG;                    // groups per warp
+  constexpr unsigned VB = Chan<T, NV>::BYTES;
   extern __shared__ uint4 smem[];
   const int LP = a.L * a.P;
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int nwarp = blockDim.x >> 5;
   const int g = lane / LPG, lig = lane % LPG;
-  int4* s_off = reinterpret_cast<int4*>(smem) + warp * (2 * GPW * (LP + 1));
-  float4* s_w = reinterpret_cast<float4*>(s_off + GPW * (LP + 1));
+  uint4* s_off = smem + warp * (2 * GPW * (LP + 1)) + g * (LP + 1);
+  float4* s_w = reinterpret_cast<float4*>(smem + warp * (2 * GPW * (LP + 1)) + GPW * (LP + 1)) + g * (LP + 1);
 
-  const int n_tiles = a.tiles_x * a.tiles_y;
-  int blk = blockIdx.x;
-  const int tile = blk % n_tiles; blk /= n_tiles;
-  const int vh = blk % (a.h * a.nchunk);
-  const int b = blk / (a.h * a.nchunk);
-  const int head = vh / a.nchunk, chunk = vh - head * a.nchunk;
-
-  const uint4* vbase = reinterpret_cast<const uint4*>(a.value) +
-                       (size_t)b * a.S * (a.h * a.Dh / VEC) + head * (a.Dh / VEC) + chunk * LPG + lig;
-  const int tq = a.tw * a.th;
+  const TileCtx c = tile_ctx(a);
+  const int vec_per_pix = a.h * a.Dh / NV;
+  const int head_vec = c.head * (a.Dh / NV) + c.chunk * LPG + lig;
+  const char* vbase =
+      opaque(reinterpret_cast<const char*>(a.value) + ((size_t)c.b * a.S * vec_per_pix + head_vec) * VB);
+  const int tq = a.th << a.tw_shift;
 
   for (int base = warp * GPW; base < tq; base += nwarp * GPW) {
+    int q;
+    const bool live = tile_query(a, c, base + g, q);
+    const int bq = c.b * a.Nq + q;
+    const size_t item = (size_t)bq * a.h + c.head;
     __syncwarp();
-    // ---- stage the taps of this warp's GPW items
-    for (int pt = lane; pt < GPW * LP; pt += 32) {
-      const int gg = pt / LP, p = pt - gg * LP;
-      int q;
-      int4 o = make_int4(0, 0, 0, 0);
+    // ---- stage the taps of this group's item: lane `lig` sets up points lig, lig+LPG, ...
+    for (int p = lig; p < LP; p += LPG) {
+      uint4 o = make_uint4(0, 0, 0, 0);
       float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tile_query(a, tile, base + gg, q)) {
-        Tap t = make_tap<T>(a, b, q, head, p);
-        if (t.any) {
-          const float wx1 = t.fx, wx0 = 1.f - t.fx, wy1 = t.fy, wy0 = 1.f - t.fy;
-          const float bw[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
-          int oo[4];
-          float ww[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            oo[i] = t.off[i] < 0 ? 0 : t.off[i];
-            ww[i] = t.off[i] < 0 ? 0.f : t.aw * bw[i];
-          }
-          o = make_int4(oo[0], oo[1], oo[2], oo[3]);
-          w = make_float4(ww[0], ww[1], ww[2], ww[3]);
-        }
+      if (live) {
+        const TapRec t = make_tap<T>(a, item, bq, p, vec_per_pix);
+        const float wx1 = t.fx * t.aw, wx0 = t.aw - wx1, wy1 = t.fy, wy0 = 1.f - t.fy;
+        o = make_uint4(t.off[0], t.off[1], t.off[2], t.off[3]);
+        w = make_float4((t.mask & 1u) ? wx0 * wy0 : 0.f, (t.mask & 2u) ? wx1 * wy0 : 0.f,
+                        (t.mask & 4u) ? wx0 * wy1 : 0.f, (t.mask & 8u) ? wx1 * wy1 : 0.f);
       }
-      s_off[gg * (LP + 1) + p] = o;
-      s_w[gg * (LP + 1) + p] = w;
+      s_off[p] = o;
+      s_w[p] = w;
     }
     __syncwarp();
     // ---- branch-free gather
-    int q;
-    const bool live = tile_query(a, tile, base + g, q);
-    float acc[VEC];
+    float acc[NV];
 #pragma unroll
-    for (int c = 0; c < VEC; ++c) acc[c] = 0.f;
-    const int4* so = s_off + g * (LP + 1);
-    const float4* sw = s_w + g * (LP + 1);
+    for (int ch = 0; ch < NV; ++ch) acc[ch] = 0.f;
 #pragma unroll 4
     for (int p = 0; p < LP; ++p) {
-      const int4 o = so[p];
-      const float4 w = sw[p];
-      const uint4 u0 = ldg128(vbase + o.x), u1 = ldg128(vbase + o.y);
-      const uint4 u2 = ldg128(vbase + o.z), u3 = ldg128(vbase + o.w);
-      float f[VEC];
-      Vec<T>::unpack(u0, f);
+      const uint4 o = s_off[p];
+      const float4 w = s_w[p];
+      float f0[NV], f1[NV], f2[NV], f3[NV];
+      Chan<T, NV>::load(addr_u32(vbase, o.x, VB), f0);
+      Chan<T, NV>::load(addr_u32(vbase, o.y, VB), f1);
+      Chan<T, NV>::load(addr_u32(vbase, o.z, VB), f2);
+      Chan<T, NV>::load(addr_u32(vbase, o.w, VB), f3);
 #pragma unroll
-      for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w.x, f[c], acc[c]);
-      Vec<T>::unpack(u1, f);
-#pragma unroll
-      for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w.y, f[c], acc[c]);
-      Vec<T>::unpack(u2, f);
-#pragma unroll
-      for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w.z, f[c], acc[c]);
-      Vec<T>::unpack(u3, f);
-#pragma unroll
-      for (int c = 0; c < VEC; ++c) acc[c] = fmaf(w.w, f[c], acc[c]);
+      for (int ch = 0; ch < NV; ++ch) {
+        acc[ch] = fmaf(w.x, f0[ch], acc[ch]);
+        acc[ch] = fmaf(w.y, f1[ch], acc[ch]);
+        acc[ch] = fmaf(w.z, f2[ch], acc[ch]);
+        acc[ch] = fmaf(w.w, f3[ch], acc[ch]);
+      }
     }
-    if (live) {
-      uint4* o = reinterpret_cast<uint4*>(a.out) +
-                 (((size_t)b * a.Nq + q) * a.h + head) * (a.Dh / VEC) + chunk * LPG + lig;
-      *o = Vec<T>::pack(acc);
-    }
+    if (live)
+      Chan<T, NV>::store(reinterpret_cast<char*>(a.out) + (item * (a.Dh / NV) + c.chunk * LPG + lig) * VB, acc);
   }
 }
 
 // ------------------------------------------------------------------ backward
-template <typename T, int LPG, int MAXT>
-__global__ void __launch_bounds__(MAXT) msda_bwd_kernel(const __grid_constant__ MsdaArgs a) {
-  constexpr int VEC = Vec<T>::N;
+template <typename T, int LPG>
+__global__ void __launch_bounds__(256) msda_bwd_kernel(const __grid_constant__ MsdaArgs a) {
+  constexpr int NV = 4;
   constexpr int GPW = 32 / LPG;
+  constexpr unsigned VB = Chan<T, NV>::BYTES;
   extern __shared__ uint4 smem[];
   const int LP = a.L * a.P;
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const int nwarp = blockDim.x >> 5;
   const int g = lane / LPG, lig = lane % LPG;
-  int4* s_off = reinterpret_cast<int4*>(smem) + warp * (2 * GPW * (LP + 1));
-  float4* s_w = reinterpret_cast<float4*>(s_off + GPW * (LP + 1));   // fx, fy, aw, -
+  uint4* s_off = smem + warp * (2 * GPW * (LP + 1)) + g * (LP + 1);
+  float4* s_w = reinterpret_cast<float4*>(smem + warp * (2 * GPW * (LP + 1)) + GPW * (LP + 1)) + g * (LP + 1);
 
-  const int n_tiles = a.tiles_x * a.tiles_y;
-  int blk = blockIdx.x;
-  const int tile = blk % n_tiles; blk /= n_tiles;
-  const int vh = blk % (a.h * a.nchunk);
-  const int b = blk / (a.h * a.nchunk);
-  const int head = vh / a.nchunk, chunk = vh - head * a.nchunk;
-
-  const int vec_per_pix = a.h * a.Dh / VEC;
-  const size_t vec0 = (size_t)b * a.S * vec_per_pix + head * (a.Dh / VEC) + chunk * LPG + lig;
-  const uint4* vbase = reinterpret_cast<const uint4*>(a.value) + vec0;
-  float* gvbase = a.grad_value ? a.grad_value + vec0 * VEC : nullptr;
-  const int tq = a.tw * a.th;
+  const TileCtx c = tile_ctx(a);
+  const int vec_per_pix = a.h * a.Dh / NV;
+  const int head_vec = c.head * (a.Dh / NV) + c.chunk * LPG + lig;
+  const size_t vec0 = (size_t)c.b * a.S * vec_per_pix + head_vec;
+  const char* vbase = opaque(reinterpret_cast<const char*>(a.value) + vec0 * VB);
+  const char* gvbase = a.grad_value ? opaque(reinterpret_cast<const char*>(a.grad_value) + vec0 * 16) : nullptr;
+  const int tq = a.th << a.tw_shift;
   const unsigned gmask = (LPG == 32) ? 0xffffffffu : (((1u << LPG) - 1u) << (g * LPG));
 
   for (int base = warp * GPW; base < tq; base += nwarp * GPW) {
-    __syncwarp();
-    for (int pt = lane; pt < GPW * LP; pt += 32) {
-      const int gg = pt / LP, p = pt - gg * LP;
-      int q;
-      int4 o = make_int4(-1, -1, -1, -1);
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (tile_query(a, tile, base + gg, q)) {
-        Tap t = make_tap<T>(a, b, q, head, p);
-        o = make_int4(t.off[0], t.off[1], t.off[2], t.off[3]);
-        w = make_float4(t.fx, t.fy, t.aw, 0.f);
-      }
-      s_off[gg * (LP + 1) + p] = o;
-      s_w[gg * (LP + 1) + p] = w;
-    }
-    __syncwarp();
     int q;
-    const bool live = tile_query(a, tile, base + g, q);
-    float go[VEC];
-#pragma unroll
-    for (int c = 0; c < VEC; ++c) go[c] = 0.f;
-    if (live) {
-      const uint4 u = ldg128(reinterpret_cast<const uint4*>(a.grad_out) +
-                             (((size_t)b * a.Nq + q) * a.h + head) * (a.Dh / VEC) + chunk * LPG + lig);
-      Vec<T>::unpack(u, go);
+    const bool live = tile_query(a, c, base + g, q);
+    const int bq = c.b * a.Nq + q;
+    const size_t item = (size_t)bq * a.h + c.head;
+    __syncwarp();
+    for (int p = lig; p < LP; p += LPG) {
+      uint4 o = make_uint4(0, 0, 0, 0);
+      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (live) {
+        const TapRec t = make_tap<T>(a, item, bq, p, vec_per_pix);
+        o = make_uint4(t.off[0], t.off[1], t.off[2], t.off[3]);
+        w = make_float4(t.fx, t.fy, t.aw, __uint_as_float(t.mask));
+      }
+      s_off[p] = o;
+      s_w[p] = w;
     }
-    const int4* so = s_off + g * (LP + 1);
-    const float4* sw = s_w + g * (LP + 1);
-    const size_t li0 = live ? (((size_t)b * a.Nq + q) * a.h + head) * LP : 0;
+    __syncwarp();
+    float go[NV];
+#pragma unroll
+    for (int ch = 0; ch < NV; ++ch) go[ch] = 0.f;
+    if (live)
+      Chan<T, NV>::load(reinterpret_cast<const char*>(a.grad_out) + (item * (a.Dh / NV) + c.chunk * LPG + lig) * VB, go);
+    const size_t li0 = item * LP;
+    int l = 0, pl = 0;                                   // level of point p, tracked without division
+    float sxl = unnormalize_scale(a.lvl_w[0], a.flags), syl = unnormalize_scale(a.lvl_h[0], a.flags);
 #pragma unroll 2
     for (int p = 0; p < LP; ++p) {
-      const int4 o = so[p];
-      const float4 w = sw[p];
-      const int offs[4] = {o.x, o.y, o.z, o.w};
+      const uint4 o = s_off[p];
+      const float4 w = s_w[p];
+      const unsigned mask = __float_as_uint(w.w);
+      const unsigned offs[4] = {o.x, o.y, o.z, o.w};
       const float wx1 = w.x, wx0 = 1.f - w.x, wy1 = w.y, wy0 = 1.f - w.y, aw = w.z;
-      const float bw[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
-      uint4 u[4];
+      float f[4][NV];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) u[i] = offs[i] >= 0 ? ldg128(vbase + offs[i]) : make_uint4(0, 0, 0, 0);
+      for (int t = 0; t < 4; ++t) Chan<T, NV>::load(addr_u32(vbase, offs[t], VB), f[t]);
       float d[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float f[VEC];
-        Vec<T>::unpack(u[i], f);
-        float s = 0.f;
+      for (int t = 0; t < 4; ++t) {
+        float s = go[0] * f[t][0];
 #pragma unroll
-        for (int c = 0; c < VEC; ++c) s = fmaf(go[c], f[c], s);
-        d[i] = s;
-        if (gvbase && offs[i] >= 0) {
-          const float wt = aw * bw[i];
-          float* dst = gvbase + (size_t)offs[i] * VEC;
+        for (int ch = 1; ch < NV; ++ch) s = fmaf(go[ch], f[t][ch], s);
+        d[t] = (mask >> t) & 1u ? s : 0.f;               // out-of-range taps read a safe line: drop them
+      }
+      if (gvbase) {
+        const float bw[4] = {wx0 * wy0, wx1 * wy0, wx0 * wy1, wx1 * wy1};
 #pragma unroll
-          for (int c = 0; c < VEC; c += 4)
-            red_add_v4(dst + c, wt * go[c], wt * go[c + 1], wt * go[c + 2], wt * go[c + 3]);
+        for (int t = 0; t < 4; ++t) {
+          const float wt = aw * bw[t];
+          float* dst = reinterpret_cast<float*>(const_cast<char*>(addr_u32(gvbase, offs[t], 16)));
+          red_add_v4_if(((mask >> t) & 1u) && wt != 0.f, dst, wt * go[0], wt * go[1], wt * go[2], wt * go[3]);
         }
       }
       // per-lane partials of d/d weight, d/d pixel_x, d/d pixel_y; reduce over the group
@@ -286,22 +323,21 @@ __global__ void __launch_bounds__(MAXT) msda_bwd_kernel(const __grid_constant__ 
         gx += __shfl_xor_sync(gmask, gx, s);
         gy += __shfl_xor_sync(gmask, gy, s);
       }
-      if (live && lig == (p % LPG)) {
-        const int l = p / a.P;
+      if (live && lig == (p & (LPG - 1))) {
         if (a.nchunk == 1) {
-          if (a.grad_loc) {
-            float2 r = make_float2(gx * unnormalize_scale(a.lvl_w[l], a.flags),
-                                   gy * unnormalize_scale(a.lvl_h[l], a.flags));
-            reinterpret_cast<float2*>(a.grad_loc)[li0 + p] = r;
-          }
-          if (a.grad_weight) Vec<T>::store1(reinterpret_cast<T*>(a.grad_weight) + li0 + p, gw);
+          if (a.grad_loc) reinterpret_cast<float2*>(a.grad_loc)[li0 + p] = make_float2(gx * sxl, gy * syl);
+          if (a.grad_weight) store_scalar(reinterpret_cast<T*>(a.grad_weight) + li0 + p, gw);
         } else {  // several channel chunks of one head add into the same slot (fp32 only)
           if (a.grad_loc) {
-            atomicAdd(a.grad_loc + 2 * (li0 + p), gx * unnormalize_scale(a.lvl_w[l], a.flags));
-            atomicAdd(a.grad_loc + 2 * (li0 + p) + 1, gy * unnormalize_scale(a.lvl_h[l], a.flags));
+            atomicAdd(a.grad_loc + 2 * (li0 + p), gx * sxl);
+            atomicAdd(a.grad_loc + 2 * (li0 + p) + 1, gy * syl);
           }
           if (a.grad_weight) atomicAdd(reinterpret_cast<float*>(a.grad_weight) + li0 + p, gw);
         }
+      }
+      if (++pl == a.P) {
+        pl = 0; ++l;
+        if (l < a.L) { sxl = unnormalize_scale(a.lvl_w[l], a.flags); syl = unnormalize_scale(a.lvl_h[l], a.flags); }
       }
     }
   }
@@ -315,70 +351,89 @@ __global__ void cast_f32_to_bf16_kernel(const float4* __restrict__ src, uint2* _
 }
 
 // ------------------------------------------------------------------ host side
-static int pick_lpg(int Dh, int vec) {
-  const int nvec = Dh / vec;
+static int pick_lpg(int Dh, int nv) {
+  const int nvec = Dh / nv;
   for (int lpg = 32; lpg >= 1; lpg >>= 1)
     if (nvec % lpg == 0) return lpg;
   return 1;
 }
 
+// tile-shape override for tuning sweeps (process-wide; 0 = default)
+static int g_tile_w = 0, g_tile_h = 0;
+
 static int fill_args(MsdaArgs& a, const int32_t* spatial_hw, const int32_t* level_start, int B, int S, int h,
-                     int Dh, int Nq, int L, int P, int query_w, int dtype, int flags) {
+                     int Dh, int Nq, int L, int P, int query_w, int dtype, int flags, int nv) {
   BEVR_REQUIRE(dtype == BEVR_F32 || dtype == BEVR_BF16, "msda: dtype must be 0 (f32) or 1 (bf16), got %d", dtype);
   BEVR_REQUIRE(B > 0 && S > 0 && h > 0 && Dh > 0 && Nq > 0 && L > 0 && P > 0, "msda: all dimensions must be > 0");
   BEVR_REQUIRE(L <= BEVR_MAX_LEVELS, "msda: at most %d levels (got %d)", BEVR_MAX_LEVELS, L);
   const int vec = dtype == BEVR_F32 ? 4 : 8;
   BEVR_REQUIRE(Dh % vec == 0, "msda: Dh*sizeof(dtype) must be a multiple of 16 bytes (Dh=%d)", Dh);
   BEVR_REQUIRE(spatial_hw && level_start, "msda: spatial_hw / level_start are NULL");
-  BEVR_REQUIRE((size_t)S * h * Dh / vec < (1u << 31), "msda: one sample's value exceeds 2^31 vectors");
+  BEVR_REQUIRE((size_t)S * h * Dh / 4 < (1ull << 32), "msda: one sample's value exceeds 2^32 vectors");
+  BEVR_REQUIRE((size_t)B * Nq < (1ull << 31), "msda: B*Nq exceeds 2^31");
   a.B = B; a.S = S; a.h = h; a.Dh = Dh; a.Nq = Nq; a.L = L; a.P = P; a.flags = flags;
+  a.p_shift = -1;
+  for (int s = 0; s < 16; ++s)
+    if ((1 << s) == P) a.p_shift = s;
   for (int l = 0; l < L; ++l) {
     a.lvl_h[l] = spatial_hw[2 * l]; a.lvl_w[l] = spatial_hw[2 * l + 1]; a.lvl_start[l] = level_start[l];
     BEVR_REQUIRE(a.lvl_h[l] > 0 && a.lvl_w[l] > 0 && a.lvl_start[l] >= 0 &&
                  a.lvl_start[l] + a.lvl_h[l] * a.lvl_w[l] <= S, "msda: level %d (%dx%d @%d) outside S=%d",
                  l, a.lvl_h[l], a.lvl_w[l], a.lvl_start[l], S);
   }
+  int tw = 8, th = 8;
+  if (g_tile_w > 0 && g_tile_h > 0) { tw = g_tile_w; th = g_tile_h; }
   if (query_w > 0) {
     BEVR_REQUIRE(Nq % query_w == 0, "msda: query_w=%d does not divide Nq=%d", query_w, Nq);
-    a.qw = query_w; a.qh = Nq / query_w; a.tw = 8; a.th = 8;
+    a.qw = query_w; a.qh = Nq / query_w;
   } else {
-    a.qw = Nq; a.qh = 1; a.tw = 64; a.th = 1;
+    a.qw = Nq; a.qh = 1; tw = tw * th; th = 1;
   }
-  a.tiles_x = (a.qw + a.tw - 1) / a.tw;
+  a.tw_shift = 0;
+  while ((2 << a.tw_shift) <= tw) ++a.tw_shift;       // round the tile width down to a power of two
+  a.th = th;
+  a.tiles_x = (a.qw + (1 << a.tw_shift) - 1) >> a.tw_shift;
   a.tiles_y = (a.qh + a.th - 1) / a.th;
-  const int lpg = pick_lpg(Dh, vec);
-  a.nchunk = Dh / (lpg * vec);
+  const int lpg = pick_lpg(Dh, nv);
+  a.nchunk = Dh / (lpg * nv);
   return 0;
 }
 
-// tile-shape override for tuning sweeps (process-wide; 0 = default)
-static int g_tile_w = 0, g_tile_h = 0, g_threads = 0;
-
-template <typename T, int LPG>
-static int launch(const MsdaArgs& a, bool bwd, cudaStream_t st) {
-  const int threads = g_threads > 0 ? g_threads : 256;
+template <typename K>
+static int launch(K kern, const MsdaArgs& a, int lpg, const char* what, cudaStream_t st) {
+  const int threads = 256;
   const int LP = a.L * a.P;
-  const size_t smem = (size_t)(threads / 32) * 2 * (32 / LPG) * (LP + 1) * 16;
+  const size_t smem = (size_t)(threads / 32) * 2 * (32 / lpg) * (LP + 1) * 16;
   BEVR_REQUIRE(smem <= 200 * 1024, "msda: L*P=%d needs %zu B of shared memory", LP, smem);
   const long long grid = (long long)a.B * a.h * a.nchunk * a.tiles_x * a.tiles_y;
   BEVR_REQUIRE(grid < (1ll << 31), "msda: grid too large");
-  auto kern = threads > 256 ? (bwd ? msda_bwd_kernel<T, LPG, 1024> : msda_fwd_kernel<T, LPG, 1024>)
-                            : (bwd ? msda_bwd_kernel<T, LPG, 256> : msda_fwd_kernel<T, LPG, 256>);
   if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   kern<<<(unsigned)grid, threads, smem, st>>>(a);
-  return check_launch(bwd ? "msda_bwd" : "msda_fwd");
+  return check_launch(what);
 }
 
-template <typename T>
-static int dispatch(const MsdaArgs& a, bool bwd, cudaStream_t st) {
-  const int lpg = pick_lpg(a.Dh, Vec<T>::N);
+template <typename T, int NV>
+static int dispatch_fwd(const MsdaArgs& a, cudaStream_t st) {
+  const int lpg = pick_lpg(a.Dh, NV);
   switch (lpg) {
-    case 32: return launch<T, 32>(a, bwd, st);
-    case 16: return launch<T, 16>(a, bwd, st);
-    case 8: return launch<T, 8>(a, bwd, st);
-    case 4: return launch<T, 4>(a, bwd, st);
-    case 2: return launch<T, 2>(a, bwd, st);
-    default: return launch<T, 1>(a, bwd, st);
+    case 32: return launch(msda_fwd_kernel<T, NV, 32>, a, 32, "msda_fwd", st);
+    case 16: return launch(msda_fwd_kernel<T, NV, 16>, a, 16, "msda_fwd", st);
+    case 8: return launch(msda_fwd_kernel<T, NV, 8>, a, 8, "msda_fwd", st);
+    case 4: return launch(msda_fwd_kernel<T, NV, 4>, a, 4, "msda_fwd", st);
+    case 2: return launch(msda_fwd_kernel<T, NV, 2>, a, 2, "msda_fwd", st);
+    default: return launch(msda_fwd_kernel<T, NV, 1>, a, 1, "msda_fwd", st);
+  }
+}
+template <typename T>
+static int dispatch_bwd(const MsdaArgs& a, cudaStream_t st) {
+  const int lpg = pick_lpg(a.Dh, 4);
+  switch (lpg) {
+    case 32: return launch(msda_bwd_kernel<T, 32>, a, 32, "msda_bwd", st);
+    case 16: return launch(msda_bwd_kernel<T, 16>, a, 16, "msda_bwd", st);
+    case 8: return launch(msda_bwd_kernel<T, 8>, a, 8, "msda_bwd", st);
+    case 4: return launch(msda_bwd_kernel<T, 4>, a, 4, "msda_bwd", st);
+    case 2: return launch(msda_bwd_kernel<T, 2>, a, 2, "msda_bwd", st);
+    default: return launch(msda_bwd_kernel<T, 1>, a, 1, "msda_bwd", st);
   }
 }
 
@@ -387,16 +442,8 @@ static int dispatch(const MsdaArgs& a, bool bwd, cudaStream_t st) {
 using namespace bevr;
 
 extern "C" void bevr_msda_set_tile(int tile_w, int tile_h, int threads) {
-  g_tile_w = tile_w; g_tile_h = tile_h; g_threads = threads;
-}
-
-static void apply_tile_override(MsdaArgs& a) {
-  if (g_tile_w > 0 && g_tile_h > 0) {
-    if (a.qh == 1) { a.tw = g_tile_w * g_tile_h; a.th = 1; }
-    else { a.tw = g_tile_w; a.th = g_tile_h; }
-    a.tiles_x = (a.qw + a.tw - 1) / a.tw;
-    a.tiles_y = (a.qh + a.th - 1) / a.th;
-  }
+  (void)threads;
+  g_tile_w = tile_w; g_tile_h = tile_h;
 }
 
 extern "C" int bevr_msda_fwd(const void* value, const int32_t* spatial_hw, const int32_t* level_start,
@@ -404,12 +451,13 @@ extern "C" int bevr_msda_fwd(const void* value, const int32_t* spatial_hw, const
                              void* out, int B, int S, int h, int Dh, int Nq, int L, int P, int query_w,
                              int dtype, int flags, void* stream) {
   MsdaArgs a = {};
-  if (int rc = fill_args(a, spatial_hw, level_start, B, S, h, Dh, Nq, L, P, query_w, dtype, flags)) return rc;
+  if (int rc = fill_args(a, spatial_hw, level_start, B, S, h, Dh, Nq, L, P, query_w, dtype, flags,
+                         dtype == BEVR_F32 ? 4 : 8))
+    return rc;
   BEVR_REQUIRE(value && sampling_loc && out, "msda_fwd: value / sampling_loc / out must not be NULL");
-  apply_tile_override(a);
   a.value = value; a.loc = sampling_loc; a.ref = ref_points; a.weight = attn_weight; a.out = out;
   cudaStream_t st = (cudaStream_t)stream;
-  return dtype == BEVR_F32 ? dispatch<float>(a, false, st) : dispatch<__nv_bfloat16>(a, false, st);
+  return dtype == BEVR_F32 ? dispatch_fwd<float, 4>(a, st) : dispatch_fwd<__nv_bfloat16, 8>(a, st);
 }
 
 extern "C" size_t bevr_msda_bwd_workspace_bytes(int B, int S, int h, int Dh, int dtype) {
@@ -422,13 +470,12 @@ extern "C" int bevr_msda_bwd(const void* value, const int32_t* spatial_hw, const
                              void* workspace, int B, int S, int h, int Dh, int Nq, int L, int P, int query_w,
                              int dtype, int flags, void* stream) {
   MsdaArgs a = {};
-  if (int rc = fill_args(a, spatial_hw, level_start, B, S, h, Dh, Nq, L, P, query_w, dtype, flags)) return rc;
+  if (int rc = fill_args(a, spatial_hw, level_start, B, S, h, Dh, Nq, L, P, query_w, dtype, flags, 4)) return rc;
   BEVR_REQUIRE(value && sampling_loc && grad_out, "msda_bwd: value / sampling_loc / grad_out must not be NULL");
   BEVR_REQUIRE(!(attn_weight == nullptr && grad_weight != nullptr), "msda_bwd: grad_weight without attn_weight");
   BEVR_REQUIRE(!(dtype == BEVR_BF16 && grad_value && !workspace), "msda_bwd: bf16 grad_value needs the fp32 workspace");
   BEVR_REQUIRE(!(a.nchunk > 1 && dtype == BEVR_BF16 && grad_weight),
-               "msda_bwd: bf16 grad_weight with Dh > 256 is not supported");
-  apply_tile_override(a);
+               "msda_bwd: bf16 grad_weight with Dh > 128 is not supported");
   cudaStream_t st = (cudaStream_t)stream;
   a.value = value; a.loc = sampling_loc; a.ref = ref_points; a.weight = attn_weight; a.grad_out = grad_out;
   a.grad_loc = grad_loc; a.grad_weight = grad_weight;
@@ -443,7 +490,7 @@ extern "C" int bevr_msda_bwd(const void* value, const int32_t* spatial_hw, const
     if (grad_loc) cudaMemsetAsync(grad_loc, 0, nl * 2 * sizeof(float), st);
     if (grad_weight) cudaMemsetAsync(grad_weight, 0, nl * sizeof(float), st);
   }
-  int rc = dtype == BEVR_F32 ? dispatch<float>(a, true, st) : dispatch<__nv_bfloat16>(a, true, st);
+  int rc = dtype == BEVR_F32 ? dispatch_bwd<float>(a, st) : dispatch_bwd<__nv_bfloat16>(a, st);
   if (rc) return rc;
   if (grad_value && dtype == BEVR_BF16) {
     cast_f32_to_bf16_kernel<<<148 * 8, 256, 0, st>>>((const float4*)workspace, (uint2*)grad_value, n / 4);

@@ -57,12 +57,18 @@ class _DeformAttnBase(nn.Module):
         self.kernel_size, self.stride, self.n_views = kernel_size, stride, n_views
         self.data_type, self.logger = data_type, logger
         self._grids = {}
-        C = self.embed_dim
+        self._drop = (attn_drop_rate, proj_drop_rate)
+
+    def _projections(self, out_in_channels):
+        """Registered after the offset nets so parameter ORDER (optimizer state) matches the reference too."""
+        C, Cg = self.embed_dim, self.n_channel_per_group
         self.proj_q = nn.Conv2d(C, C, 1)          # defined but never applied, as in the reference
         self.proj_k = nn.Conv2d(C, C, 1)
         self.proj_v = nn.Conv2d(C, C, 1)
-        self.proj_drop_rate = nn.Dropout(proj_drop_rate, inplace=True)
-        self.attn_drop_rate = nn.Dropout(attn_drop_rate, inplace=True)
+        self.proj_out = nn.Conv2d(out_in_channels, C, 1)
+        self.proj_views = nn.Conv2d(Cg * self.n_views, Cg, 1)     # unused, kept for the state_dict
+        self.proj_drop_rate = nn.Dropout(self._drop[1], inplace=True)
+        self.attn_drop_rate = nn.Dropout(self._drop[0], inplace=True)
 
     @torch.no_grad()
     def _get_normalized_grid(self, H, W, B, device):
@@ -111,8 +117,7 @@ class TSADeformableAttention(_DeformAttnBase):
         Cg = self.n_channel_per_group
         pad = kernel_size // 2 if kernel_size != stride else 0
         self.conv_offset = _offset_net(Cg, Cg, 2, kernel_size, stride, pad)
-        self.proj_out = nn.Conv2d(self.embed_dim, self.embed_dim, 1)
-        self.proj_views = nn.Conv2d(Cg * n_views, Cg, 1)          # unused, kept for the state_dict
+        self._projections(self.embed_dim)
         self.rpe_table = nn.Parameter(torch.zeros(n_heads, self.bev_h * 2 - 1, self.bev_w * 2 - 1))
         nn.init.trunc_normal_(self.rpe_table, std=0.01)
 
@@ -145,8 +150,7 @@ class SCADeformableAttention(_DeformAttnBase):
         self.conv_offset_m0 = _offset_net(Cg, Cg * D, D, 1, 1, 0)
         self.conv_offset_m1 = _offset_net(Cg, Cg * D, 2 * D, 1, 1, 0)
         self.conv_offset_m2 = _offset_net(Cg, Cg * D, 2 * D, 1, 1, 0)
-        self.proj_out = nn.Conv2d(self.embed_dim * n_views, self.embed_dim, 1)
-        self.proj_views = nn.Conv2d(Cg * n_views, Cg, 1)
+        self._projections(self.embed_dim * n_views)
         self.rpe_table = nn.Parameter(
             torch.zeros(n_heads, self.query_height * 2 - 1, self.query_width * D * 2 - 1))
         nn.init.trunc_normal_(self.rpe_table, std=0.01)

@@ -5,6 +5,11 @@ import torch
 
 from util import FP32_TOL, load_golden, rel_err
 
+# The offset nets and 1x1 projections stay PyTorch/cuDNN.  cuDNN convolutions default to TF32
+# on sm_100 (~1e-3 relative), which would mask the 1e-4 parity of the kernels under test -> force fp32 convs.
+torch.backends.cudnn.allow_tf32 = False
+torch.backends.cuda.matmul.allow_tf32 = False
+
 TSA_CASES = ["tsa_s1", "tsa_s2", "tsa_self", "tsa_clamp"]
 SCA_CASES = ["sca_d5", "sca_g2", "sca_clamp"]
 
