@@ -23,8 +23,9 @@ struct RpeArgs {
   float scale;
 };
 
-constexpr int DH = 32;
-constexpr int PAD = DH + 4;   // smem row stride (floats): keeps float4 alignment, spreads banks
+// DH (channels per head) is a template parameter of every kernel: 32 (the reference, encoder.py:23-39) and 16.
+// Shared-memory row stride is DH + 4 floats: keeps float4 alignment and spreads the banks.
+#define PAD (DH + 4)
 
 // normalised query-grid coordinate, bit-identical to torch's arange -> /(n-1) -> *2 -> -1
 __device__ __forceinline__ float grid_coord(int i, int n) {
@@ -32,38 +33,44 @@ __device__ __forceinline__ float grid_coord(int i, int n) {
 }
 
 struct Bilin {
-  int off[4];     // table offsets of nw, ne, sw, se (or -1)
-  float wx0, wx1, wy0, wy1;
+  int off[4];             // table offsets of nw, ne, sw, se (always in range: clamped)
+  float wx0, wx1, wy0, wy1;   // bilinear weights (unmasked)
+  float mx0, mx1, my0, my1;   // 1 if that column / row of taps lies inside the table, else 0
 };
 
-// coordinates in the rpe table of the displacement (query - key)/2, as grid_sample(align_corners=True)
+// coordinates in the rpe table of the displacement (query - key)/2, as grid_sample(align_corners=True).
+// Taps outside the table contribute zero (padding_mode="zeros"): their addresses are clamped to stay
+// loadable and their row/column mask is 0 -- 4 unconditional loads, no per-tap branches.
 __device__ __forceinline__ Bilin rpe_taps(float qy, float qx, float py, float px, int Rh, int Rw) {
   const float dy = (qy - py) * 0.5f, dx = (qx - px) * 0.5f;
   const float ix = ((dx + 1.f) / 2.f) * (float)(Rw - 1);
   const float iy = ((dy + 1.f) / 2.f) * (float)(Rh - 1);
   Bilin b;
-  const bool any = (ix > -1.f) && (ix < (float)Rw) && (iy > -1.f) && (iy < (float)Rh);
   const float x0f = floorf(ix), y0f = floorf(iy);
   b.wx1 = ix - x0f; b.wx0 = (x0f + 1.f) - ix;
   b.wy1 = iy - y0f; b.wy0 = (y0f + 1.f) - iy;
-  const int x0 = any ? (int)x0f : -2, y0 = any ? (int)y0f : -2;
-#pragma unroll
-  for (int t = 0; t < 4; ++t) {
-    const int xi = x0 + (t & 1), yi = y0 + (t >> 1);
-    b.off[t] = (xi >= 0 && xi < Rw && yi >= 0 && yi < Rh) ? yi * Rw + xi : -1;
-  }
+  const float xm = (float)(Rw - 1), ym = (float)(Rh - 1);
+  b.mx0 = (x0f >= 0.f && x0f <= xm) ? 1.f : 0.f;
+  b.mx1 = (x0f >= -1.f && x0f <= xm - 1.f) ? 1.f : 0.f;
+  b.my0 = (y0f >= 0.f && y0f <= ym) ? 1.f : 0.f;
+  b.my1 = (y0f >= -1.f && y0f <= ym - 1.f) ? 1.f : 0.f;
+  const int x0 = (int)fminf(fmaxf(x0f, 0.f), xm), x1 = (int)fminf(fmaxf(x0f + 1.f, 0.f), xm);
+  const int y0 = (int)fminf(fmaxf(y0f, 0.f), ym) * Rw, y1 = (int)fminf(fmaxf(y0f + 1.f, 0.f), ym) * Rw;
+  b.off[0] = y0 + x0; b.off[1] = y0 + x1; b.off[2] = y1 + x0; b.off[3] = y1 + x1;
   return b;
 }
 
+// bias value; tapv receives the MASKED tap values (0 for taps outside the table)
 __device__ __forceinline__ float rpe_bias(const float* __restrict__ table, const Bilin& b, float* tapv) {
-#pragma unroll
-  for (int t = 0; t < 4; ++t) tapv[t] = b.off[t] >= 0 ? __ldg(table + b.off[t]) : 0.f;
-  return tapv[0] * (b.wx0 * b.wy0) + tapv[1] * (b.wx1 * b.wy0) + tapv[2] * (b.wx0 * b.wy1) +
-         tapv[3] * (b.wx1 * b.wy1);
+  tapv[0] = __ldg(table + b.off[0]) * (b.mx0 * b.my0);
+  tapv[1] = __ldg(table + b.off[1]) * (b.mx1 * b.my0);
+  tapv[2] = __ldg(table + b.off[2]) * (b.mx0 * b.my1);
+  tapv[3] = __ldg(table + b.off[3]) * (b.mx1 * b.my1);
+  return b.wy0 * (b.wx0 * tapv[0] + b.wx1 * tapv[1]) + b.wy1 * (b.wx0 * tapv[2] + b.wx1 * tapv[3]);
 }
 
 // stage rows [j0, j0+T) of a channel-major (DH, n) matrix as smem[T][PAD] (zero beyond n)
-template <int T>
+template <int T, int DH>
 __device__ __forceinline__ void stage_transposed(float* __restrict__ dst, const float* __restrict__ src, int n,
                                                  int j0, float mul) {
   for (int idx = threadIdx.x; idx < T * DH; idx += blockDim.x) {
@@ -73,28 +80,35 @@ __device__ __forceinline__ void stage_transposed(float* __restrict__ dst, const 
   }
 }
 
-__device__ __forceinline__ float dot32(const float* reg, const float* __restrict__ srow) {
-  float s = 0.f;
+// 32-channel dot product / axpy against a shared-memory row with packed FFMA2 (two fp32 FMAs per issue
+// slot on sm_100: the kernels of this file are FMA-issue bound).  Register operands are float2 pairs.
+template <int DH>
+__device__ __forceinline__ float dot32(const float2* reg, const float* __restrict__ srow) {
+  float2 s = make_float2(0.f, 0.f);
 #pragma unroll
-  for (int c = 0; c < DH; c += 4) {
-    const float4 kk = *reinterpret_cast<const float4*>(srow + c);
-    s = fmaf(reg[c], kk.x, s); s = fmaf(reg[c + 1], kk.y, s);
-    s = fmaf(reg[c + 2], kk.z, s); s = fmaf(reg[c + 3], kk.w, s);
+  for (int c = 0; c < DH / 4; ++c) {
+    const float4 kk = *reinterpret_cast<const float4*>(srow + 4 * c);
+    s = __ffma2_rn(reg[2 * c], make_float2(kk.x, kk.y), s);
+    s = __ffma2_rn(reg[2 * c + 1], make_float2(kk.z, kk.w), s);
   }
-  return s;
+  return s.x + s.y;
 }
-__device__ __forceinline__ void axpy32(float* acc, float a, const float* __restrict__ srow) {
+template <int DH>
+__device__ __forceinline__ void axpy32(float2* acc, float a, const float* __restrict__ srow) {
+  const float2 a2 = make_float2(a, a);
 #pragma unroll
-  for (int c = 0; c < DH; c += 4) {
-    const float4 vv = *reinterpret_cast<const float4*>(srow + c);
-    acc[c] = fmaf(a, vv.x, acc[c]); acc[c + 1] = fmaf(a, vv.y, acc[c + 1]);
-    acc[c + 2] = fmaf(a, vv.z, acc[c + 2]); acc[c + 3] = fmaf(a, vv.w, acc[c + 3]);
+  for (int c = 0; c < DH / 4; ++c) {
+    const float4 vv = *reinterpret_cast<const float4*>(srow + 4 * c);
+    acc[2 * c] = __ffma2_rn(a2, make_float2(vv.x, vv.y), acc[2 * c]);
+    acc[2 * c + 1] = __ffma2_rn(a2, make_float2(vv.z, vv.w), acc[2 * c + 1]);
   }
 }
+__device__ __forceinline__ float& lane_elem(float2* r, int c) { return (c & 1) ? r[c >> 1].y : r[c >> 1].x; }
 
 // ------------------------------------------------------------------ forward (thread = query row)
 constexpr int TQ = 128, TK = 64, CH = 16;
 
+template <int DH>
 __global__ void __launch_bounds__(TQ) rpe_attn_fwd_kernel(const __grid_constant__ RpeArgs a) {
   __shared__ __align__(16) float sK[TK * PAD];
   __shared__ __align__(16) float sV[TK * PAD];
@@ -107,11 +121,11 @@ __global__ void __launch_bounds__(TQ) rpe_attn_fwd_kernel(const __grid_constant_
   const float* vb = a.v + (size_t)bh * DH * a.Ns;
   const float2* pb = reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns;
 
-  float qr[DH], o[DH];
+  float2 qr[DH / 2], o[DH / 2];
 #pragma unroll
   for (int c = 0; c < DH; ++c) {
-    qr[c] = live ? __ldg(a.q + ((size_t)bh * DH + c) * a.Nq + i) * a.scale : 0.f;
-    o[c] = 0.f;
+    lane_elem(qr, c) = live ? __ldg(a.q + ((size_t)bh * DH + c) * a.Nq + i) * a.scale : 0.f;
+    lane_elem(o, c) = 0.f;
   }
   const int iy = i / a.Wq, ixq = i - iy * a.Wq;
   const float qy = grid_coord(iy, a.Hq), qx = grid_coord(ixq, a.Wq);
@@ -119,8 +133,8 @@ __global__ void __launch_bounds__(TQ) rpe_attn_fwd_kernel(const __grid_constant_
 
   for (int j0 = 0; j0 < a.Ns; j0 += TK) {
     __syncthreads();
-    stage_transposed<TK>(sK, kb, a.Ns, j0, 1.f);
-    stage_transposed<TK>(sV, vb, a.Ns, j0, 1.f);
+    stage_transposed<TK, DH>(sK, kb, a.Ns, j0, 1.f);
+    stage_transposed<TK, DH>(sV, vb, a.Ns, j0, 1.f);
     for (int jj = threadIdx.x; jj < TK; jj += blockDim.x)
       sPos[jj] = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
     __syncthreads();
@@ -134,7 +148,7 @@ __global__ void __launch_bounds__(TQ) rpe_attn_fwd_kernel(const __grid_constant_
         const float2 p = sPos[jc + jj];
         const Bilin b = rpe_taps(qy, qx, p.x, p.y, a.Rh, a.Rw);
         float tv[4];
-        const float sc = dot32(qr, sK + (jc + jj) * PAD) + rpe_bias(table, b, tv);
+        const float sc = dot32<DH>(qr, sK + (jc + jj) * PAD) + rpe_bias(table, b, tv);
         s[jj] = (j0 + jc + jj < a.Ns) ? sc : -INFINITY;
         mx = fmaxf(mx, s[jj]);
       }
@@ -142,12 +156,12 @@ __global__ void __launch_bounds__(TQ) rpe_attn_fwd_kernel(const __grid_constant_
       const float corr = __expf(m - mn);
       l *= corr;
 #pragma unroll
-      for (int c = 0; c < DH; ++c) o[c] *= corr;
+      for (int c = 0; c < DH / 2; ++c) { o[c].x *= corr; o[c].y *= corr; }
 #pragma unroll
       for (int jj = 0; jj < CH; ++jj) {
         const float p = __expf(s[jj] - mn);
         l += p;
-        axpy32(o, p, sV + (jc + jj) * PAD);
+        axpy32<DH>(o, p, sV + (jc + jj) * PAD);
       }
       m = mn;
     }
@@ -155,13 +169,14 @@ __global__ void __launch_bounds__(TQ) rpe_attn_fwd_kernel(const __grid_constant_
   if (live) {
     const float inv = 1.f / l;
 #pragma unroll
-    for (int c = 0; c < DH; ++c) a.o_out[((size_t)bh * DH + c) * a.Nq + i] = o[c] * inv;
+    for (int c = 0; c < DH; ++c) a.o_out[((size_t)bh * DH + c) * a.Nq + i] = lane_elem(o, c) * inv;
     a.o_lse[(size_t)bh * a.Nq + i] = m + logf(l);
   }
 }
 
 // ------------------------------------------------------------------ backward
 // delta_i = sum_c dO[c][i] * O[c][i]
+template <int DH>
 __global__ void __launch_bounds__(256) rpe_delta_kernel(const __grid_constant__ RpeArgs a) {
   const int bh = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= a.Nq) return;
@@ -175,6 +190,7 @@ __global__ void __launch_bounds__(256) rpe_delta_kernel(const __grid_constant__ 
 }
 
 // dQ: thread = query row, streams K/V tiles
+template <int DH>
 __global__ void __launch_bounds__(TQ) rpe_attn_bwd_dq_kernel(const __grid_constant__ RpeArgs a) {
   __shared__ __align__(16) float sK[TK * PAD];
   __shared__ __align__(16) float sV[TK * PAD];
@@ -187,13 +203,13 @@ __global__ void __launch_bounds__(TQ) rpe_attn_bwd_dq_kernel(const __grid_consta
   const float* vb = a.v + (size_t)bh * DH * a.Ns;
   const float2* pb = reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns;
 
-  float qr[DH], go[DH], dq[DH];
+  float2 qr[DH / 2], go[DH / 2], dq[DH / 2];
 #pragma unroll
   for (int c = 0; c < DH; ++c) {
     const size_t idx = ((size_t)bh * DH + c) * a.Nq + i;
-    qr[c] = live ? __ldg(a.q + idx) * a.scale : 0.f;
-    go[c] = live ? __ldg(a.grad_out + idx) : 0.f;
-    dq[c] = 0.f;
+    lane_elem(qr, c) = live ? __ldg(a.q + idx) * a.scale : 0.f;
+    lane_elem(go, c) = live ? __ldg(a.grad_out + idx) : 0.f;
+    lane_elem(dq, c) = 0.f;
   }
   const float lse = live ? __ldg(a.lse + (size_t)bh * a.Nq + i) : 0.f;
   const float delta = live ? __ldg(a.delta + (size_t)bh * a.Nq + i) : 0.f;
@@ -202,8 +218,8 @@ __global__ void __launch_bounds__(TQ) rpe_attn_bwd_dq_kernel(const __grid_consta
 
   for (int j0 = 0; j0 < a.Ns; j0 += TK) {
     __syncthreads();
-    stage_transposed<TK>(sK, kb, a.Ns, j0, 1.f);
-    stage_transposed<TK>(sV, vb, a.Ns, j0, 1.f);
+    stage_transposed<TK, DH>(sK, kb, a.Ns, j0, 1.f);
+    stage_transposed<TK, DH>(sV, vb, a.Ns, j0, 1.f);
     for (int jj = threadIdx.x; jj < TK; jj += blockDim.x)
       sPos[jj] = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
     __syncthreads();
@@ -213,21 +229,22 @@ __global__ void __launch_bounds__(TQ) rpe_attn_bwd_dq_kernel(const __grid_consta
       const float2 p = sPos[jj];
       const Bilin b = rpe_taps(qy, qx, p.x, p.y, a.Rh, a.Rw);
       float tv[4];
-      const float s = dot32(qr, sK + jj * PAD) + rpe_bias(table, b, tv);
+      const float s = dot32<DH>(qr, sK + jj * PAD) + rpe_bias(table, b, tv);
       const float pr = __expf(s - lse);
-      const float dp = dot32(go, sV + jj * PAD);
-      axpy32(dq, pr * (dp - delta), sK + jj * PAD);
+      const float dp = dot32<DH>(go, sV + jj * PAD);
+      axpy32<DH>(dq, pr * (dp - delta), sK + jj * PAD);
     }
   }
   if (live) {
 #pragma unroll
-    for (int c = 0; c < DH; ++c) a.grad_q[((size_t)bh * DH + c) * a.Nq + i] = dq[c] * a.scale;
+    for (int c = 0; c < DH; ++c) a.grad_q[((size_t)bh * DH + c) * a.Nq + i] = lane_elem(dq, c) * a.scale;
   }
 }
 
 // dK, dV, dpos, drpe: thread = key column, streams Q/dO tiles
 constexpr int TKB = 128, TQB = 32;
 
+template <int DH>
 __global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_constant__ RpeArgs a) {
   __shared__ __align__(16) float sQ[TQB * PAD];
   __shared__ __align__(16) float sG[TQB * PAD];
@@ -240,13 +257,13 @@ __global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_cons
   const float* qb = a.q + (size_t)bh * DH * a.Nq;
   const float* gb = a.grad_out + (size_t)bh * DH * a.Nq;
 
-  float kr[DH], vr[DH], dk[DH], dv[DH];
+  float2 kr[DH / 2], vr[DH / 2], dk[DH / 2], dv[DH / 2];
 #pragma unroll
   for (int c = 0; c < DH; ++c) {
     const size_t idx = ((size_t)bh * DH + c) * a.Ns + j;
-    kr[c] = live ? __ldg(a.k + idx) : 0.f;
-    vr[c] = live ? __ldg(a.v + idx) : 0.f;
-    dk[c] = 0.f; dv[c] = 0.f;
+    lane_elem(kr, c) = live ? __ldg(a.k + idx) : 0.f;
+    lane_elem(vr, c) = live ? __ldg(a.v + idx) : 0.f;
+    lane_elem(dk, c) = 0.f; lane_elem(dv, c) = 0.f;
   }
   float2 pj = make_float2(0.f, 0.f);
   if (live) pj = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns + j);
@@ -255,8 +272,8 @@ __global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_cons
 
   for (int i0 = 0; i0 < a.Nq; i0 += TQB) {
     __syncthreads();
-    stage_transposed<TQB>(sQ, qb, a.Nq, i0, a.scale);
-    stage_transposed<TQB>(sG, gb, a.Nq, i0, 1.f);
+    stage_transposed<TQB, DH>(sQ, qb, a.Nq, i0, a.scale);
+    stage_transposed<TQB, DH>(sG, gb, a.Nq, i0, 1.f);
     for (int ii = threadIdx.x; ii < TQB; ii += blockDim.x) {
       const int i = i0 + ii;
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -275,20 +292,21 @@ __global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_cons
       const float4 r = sRow[ii];
       const Bilin b = rpe_taps(r.x, r.y, pj.x, pj.y, a.Rh, a.Rw);
       float tv[4];
-      const float s = dot32(kr, sQ + ii * PAD) + rpe_bias(table, b, tv);
+      const float s = dot32<DH>(kr, sQ + ii * PAD) + rpe_bias(table, b, tv);
       const float pr = __expf(s - r.z);
-      axpy32(dv, pr, sG + ii * PAD);
-      const float dp = dot32(vr, sG + ii * PAD);
+      axpy32<DH>(dv, pr, sG + ii * PAD);
+      const float dp = dot32<DH>(vr, sG + ii * PAD);
       const float ds = pr * (dp - r.w);
-      axpy32(dk, ds, sQ + ii * PAD);
+      axpy32<DH>(dk, ds, sQ + ii * PAD);
       if (want_bias_grad) {
         gix = fmaf(ds, b.wy0 * (tv[1] - tv[0]) + b.wy1 * (tv[3] - tv[2]), gix);
         giy = fmaf(ds, b.wx0 * (tv[2] - tv[0]) + b.wx1 * (tv[3] - tv[1]), giy);
         if (gtable) {
-          const float w[4] = {b.wx0 * b.wy0, b.wx1 * b.wy0, b.wx0 * b.wy1, b.wx1 * b.wy1};
+          const float w[4] = {b.wx0 * b.wy0 * (b.mx0 * b.my0), b.wx1 * b.wy0 * (b.mx1 * b.my0),
+                              b.wx0 * b.wy1 * (b.mx0 * b.my1), b.wx1 * b.wy1 * (b.mx1 * b.my1)};
 #pragma unroll
           for (int t = 0; t < 4; ++t)
-            if (b.off[t] >= 0) atomicAdd(gtable + b.off[t], ds * w[t]);
+            if (w[t] != 0.f) atomicAdd(gtable + b.off[t], ds * w[t]);
         }
       }
     }
@@ -297,8 +315,8 @@ __global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_cons
 #pragma unroll
     for (int c = 0; c < DH; ++c) {
       const size_t idx = ((size_t)bh * DH + c) * a.Ns + j;
-      if (a.grad_k) a.grad_k[idx] = dk[c];    // sQ already carries `scale`
-      if (a.grad_v) a.grad_v[idx] = dv[c];
+      if (a.grad_k) a.grad_k[idx] = lane_elem(dk, c);    // sQ already carries `scale`
+      if (a.grad_v) a.grad_v[idx] = lane_elem(dv, c);
     }
     if (a.grad_pos) {
       // table coord = (Rx-1) * ((q - pos)/4 + 1/2)  ->  d coord / d pos = -(Rx-1)/4
@@ -310,7 +328,7 @@ __global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_cons
 }
 
 static int validate(int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw) {
-  BEVR_REQUIRE(Dh == DH, "rpe_attn: only Dh == 32 is built (got %d)", Dh);
+  BEVR_REQUIRE(Dh == 32 || Dh == 16, "rpe_attn: only Dh == 32 and Dh == 16 are built (got %d)", Dh);
   BEVR_REQUIRE(BH > 0 && h > 0 && hpg > 0 && BH % h == 0 && h % hpg == 0, "rpe_attn: bad BH=%d h=%d hpg=%d", BH, h, hpg);
   BEVR_REQUIRE(Hq > 1 && Wq > 1 && Ns > 0 && Rh > 0 && Rw > 0, "rpe_attn: bad sizes Hq=%d Wq=%d Ns=%d Rh=%d Rw=%d",
                Hq, Wq, Ns, Rh, Rw);
@@ -332,7 +350,8 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
   a.scale = scale;
   dim3 grid((a.Nq + TQ - 1) / TQ, BH);
-  rpe_attn_fwd_kernel<<<grid, TQ, 0, (cudaStream_t)stream>>>(a);
+  if (Dh == 32) rpe_attn_fwd_kernel<32><<<grid, TQ, 0, (cudaStream_t)stream>>>(a);
+  else rpe_attn_fwd_kernel<16><<<grid, TQ, 0, (cudaStream_t)stream>>>(a);
   return check_launch("rpe_attn_fwd");
 }
 
@@ -350,14 +369,17 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
   a.scale = scale;
   cudaStream_t st = (cudaStream_t)stream;
-  rpe_delta_kernel<<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
+  if (Dh == 32) rpe_delta_kernel<32><<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
+  else rpe_delta_kernel<16><<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
   if (int rc = check_launch("rpe_attn_bwd delta")) return rc;
   if (grad_q) {
-    rpe_attn_bwd_dq_kernel<<<dim3((a.Nq + TQ - 1) / TQ, BH), TQ, 0, st>>>(a);
+    if (Dh == 32) rpe_attn_bwd_dq_kernel<32><<<dim3((a.Nq + TQ - 1) / TQ, BH), TQ, 0, st>>>(a);
+    else rpe_attn_bwd_dq_kernel<16><<<dim3((a.Nq + TQ - 1) / TQ, BH), TQ, 0, st>>>(a);
     if (int rc = check_launch("rpe_attn_bwd dq")) return rc;
   }
   if (grad_k || grad_v || grad_rpe || grad_pos) {
-    rpe_attn_bwd_dkv_kernel<<<dim3((Ns + TKB - 1) / TKB, BH), TKB, 0, st>>>(a);
+    if (Dh == 32) rpe_attn_bwd_dkv_kernel<32><<<dim3((Ns + TKB - 1) / TKB, BH), TKB, 0, st>>>(a);
+    else rpe_attn_bwd_dkv_kernel<16><<<dim3((Ns + TKB - 1) / TKB, BH), TKB, 0, st>>>(a);
     if (int rc = check_launch("rpe_attn_bwd dkv")) return rc;
   }
   return 0;

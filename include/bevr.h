@@ -115,7 +115,7 @@ int bevr_project_points(const float* points, const float* cam_T, const float* K,
  *   out      dev f32 (BH, Dh, Nq)
  *   lse      dev f32 (BH, Nq)         log-sum-exp per row (saved for backward)
  *   hpg      heads per group (head bh uses pos[bh / hpg], table rpe[bh % h])
- * Requires Dh == 32 (the reference uses 32 channels per head everywhere, encoder.py:23-39).
+ * Requires Dh == 32 (the reference uses 32 channels per head everywhere, encoder.py:23-39) or Dh == 16.
  */
 int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe,
                       const float* pos, float* out, float* lse, int BH, int h, int hpg, int Dh,

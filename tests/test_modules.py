@@ -57,9 +57,16 @@ def test_modules_fail_loudly_without_cuda():
 
 
 def _check_grads(m, gp):
+    # proj_k.bias has a mathematically ZERO gradient (a key bias shifts every logit of a row equally and the
+    # softmax cancels it); the reference value is rounding noise ~1e-8, so such tensors are compared on the
+    # scale of the largest parameter gradient instead of on their own.
+    scale = max(float(v.abs().max()) for v in gp.values())
     for k_, ref in gp.items():
         got = dict(m.named_parameters())[k_].grad
         assert got is not None, k_
+        if float(ref.abs().max()) < 1e-5 * scale:
+            assert float(got.abs().max()) < 1e-5 * scale, k_
+            continue
         e = rel_err(got.cpu(), ref)
         assert e < FP32_TOL, f"grad {k_}: {e:.3e}"
     for k_, p in m.named_parameters():            # parameters the reference never uses stay grad-free

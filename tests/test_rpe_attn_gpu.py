@@ -8,9 +8,8 @@ from util import FP32_TOL, rel_err
 pytestmark = pytest.mark.gpu
 
 
-def _case(B, h, g, Hq, Wq, Hk, Wk, Rw_mul, seed, spread):
+def _case(B, h, g, Hq, Wq, Hk, Wk, Rw_mul, seed, spread, Dh=32):
     torch.manual_seed(seed)
-    Dh = 32
     Nq, Ns = Hq * Wq, Hk * Wk
     q = torch.randn(B * h, Dh, Nq)
     k = torch.randn(B * h, Dh, Ns)
@@ -42,6 +41,20 @@ def test_rpe_attention_matches_dense_oracle(B, h, g, Hq, Wq, Hk, Wk, mul, spread
     for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, cpu):
         e = rel_err(a.grad.cpu(), b.grad)
         assert e < FP32_TOL, f"grad_{name}: {e:.3e}"
+
+
+def test_rpe_attention_dh16():
+    import bevrender_b200 as bb
+    q, k, v, rpe, pos, go = _case(2, 4, 1, 12, 12, 12, 12, 1, 3, 0.1, Dh=16)
+    cpu = [t.clone().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    ref = oda.rpe_attention_dense(*cpu, 12, 12, 1, 16 ** -0.5)
+    ref.backward(go)
+    dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    out = bb.rpe_attention(*dev, 12, 12, 1)
+    out.backward(go.cuda())
+    assert rel_err(out.cpu(), ref) < FP32_TOL
+    for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, cpu):
+        assert rel_err(a.grad.cpu(), b.grad) < FP32_TOL, name
 
 
 def test_rpe_attention_large_rows_vs_chunked_oracle():
