@@ -115,11 +115,15 @@ int bevr_project_points(const float* points, const float* cam_T, const float* K,
  *   out      dev f32 (BH, Dh, Nq)
  *   lse      dev f32 (BH, Nq)         log-sum-exp per row (saved for backward)
  *   hpg      heads per group (head bh uses pos[bh / hpg], table rpe[bh % h])
+ *   workspace dev, bevr_rpe_attn_workspace_bytes(h, Rh, Rw, backward) bytes: holds the zero-padded
+ *            copy of the table the kernels sample (and, for backward, its padded gradient)
  * Requires Dh == 32 (the reference uses 32 channels per head everywhere, encoder.py:23-39) or Dh == 16.
  */
+size_t bevr_rpe_attn_workspace_bytes(int h, int Rh, int Rw, int backward);
 int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe,
-                      const float* pos, float* out, float* lse, int BH, int h, int hpg, int Dh,
-                      int Hq, int Wq, int Ns, int Rh, int Rw, float scale, void* stream);
+                      const float* pos, float* out, float* lse, void* workspace, int BH, int h,
+                      int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw, float scale,
+                      void* stream);
 
 /* Backward of K3.  grad_rpe (h,Rh,Rw) and grad_pos (BH/hpg,Ns,2) are ACCUMULATED into
  * (caller zero-fills); grad_q/grad_k/grad_v are overwritten.  Any grad pointer may be NULL.
@@ -128,8 +132,8 @@ int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const floa
 int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v, const float* rpe,
                       const float* pos, const float* out, const float* lse, const float* grad_out,
                       float* grad_q, float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos,
-                      float* delta_ws, int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns,
-                      int Rh, int Rw, float scale, void* stream);
+                      float* delta_ws, void* workspace, int BH, int h, int hpg, int Dh, int Hq,
+                      int Wq, int Ns, int Rh, int Rw, float scale, void* stream);
 
 #ifdef __cplusplus
 }
