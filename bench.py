@@ -128,6 +128,81 @@ def workload_config(B, dtype):
             "no explicit flush", "parallelism": "batch-sharded, no data-path collective"}
 
 
+def run_train(args):
+    """--workload train (BASELINE.json config 5): end-to-end training step of the caller-side harness
+    (stem -> 6 x [TSA, SCA] encoder layers with the drop-in modules -> render head; MSE loss, AdamW, clip 1.0;
+    window of 4 frames = 3 history passes without gradient + 1 pass with gradient), batch-data-parallel with the
+    flat-bucket NCCL gradient allreduce.  Metric: training samples/s, whole job."""
+    import torch.distributed as dist
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from bevrender_b200.dp import FlatGradAllReduce, live_named_parameters
+    from bevrender_b200.harness import BevHarness
+    torch.backends.cudnn.allow_tf32 = True           # the PyTorch convolutions of the harness, as torch defaults
+    torch.manual_seed(0)
+    B, T, n = args.batch, 4, args.bev
+    model = BevHarness(n=n, c=64, heads=2, depth=5, layers=6, batch=B, device=dev).to(dev)
+    live = [p for _, p in live_named_parameters(model)]
+    for name, p in model.named_parameters():
+        if all(p is not q for q in live):
+            p.requires_grad_(False)
+    opt = torch.optim.AdamW(live, lr=1e-4, weight_decay=1e-2)
+    red = FlatGradAllReduce(live, n_buckets=2)
+    g = torch.Generator().manual_seed(1 + rank)
+    frames_h = torch.rand(B, T, 3, 128, 160, generator=g).pin_memory()
+    target_h = torch.rand(B, 3, 224, 224, generator=g).pin_memory()
+
+    def step():
+        frames = frames_h.to(dev, non_blocking=True)
+        target = target_h.to(dev, non_blocking=True)
+        red.reset()
+        loss = torch.nn.functional.mse_loss(model(frames), target)
+        loss.backward()
+        red.finish()
+        torch.nn.utils.clip_grad_norm_(live, 1.0)
+        opt.step()
+        return loss
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record()
+        for _ in range(args.steps):
+            loss = step()
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms /= args.steps
+    if rank == 0:
+        nparam = sum(p.numel() for p in live)
+        print(json.dumps({"metric": "train samples/s", "value": world * B / (ms * 1e-3), "unit": "samples/s",
+                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
+                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+                          "data": "synthetic", "loss": float(loss),
+                          "config": {"workload": "config5: harness training step, bev %d, 6 layers, window 4, "
+                                     "image 128x160, C=64, 2 heads, D=5" % n, "batch_per_gpu": B,
+                                     "parallelism": "dp%d, flat fp32 gradient bucket (%d params, %.1f MB), 2 NCCL "
+                                     "allreduce(AVG) launches overlapped with backward" % (world, nparam, nparam * 4 / 1e6)},
+                          "clocks": clk.summary()}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -139,9 +214,14 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer leg")
     ap.add_argument("--tile", default="", help="tuning: tile_w,tile_h,threads")
+    ap.add_argument("--workload", default="msda", choices=["msda", "train"],
+                    help="msda = BASELINE config 2 (the contract line); train = config 5 harness training step")
+    ap.add_argument("--bev", type=int, default=56, help="--workload train: BEV grid size")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
+    if args.workload == "train":
+        return run_train(args)
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -248,21 +328,17 @@ def main():
                         "note": "includes the grad_value zero-fill (and the bf16 cast) the entry point enqueues"},
                 "fwd_bwd_frac": (ab_fwd + ab_bwd) / (ms_step * 1e-3) / 1e9 / peak}
 
-    # ---- end-to-end leg: HOST pinned inputs -> H2D -> fwd+bwd -> D2H of every result, per step
+    # ---- end-to-end leg: HOST pinned inputs -> H2D -> fwd+bwd -> D2H of every result, per step, through the
+    # host-buffer entry point (per-sample chunks pipelined over H2D / compute / D2H streams)
+    from bevrender_b200.host_pipeline import HostMsdaPipeline
     h_out = {k: torch.empty(t.shape, dtype=t.dtype).pin_memory() for k, t in
              (("out", out), ("grad_value", gv), ("grad_loc", gl), ("grad_weight", gw))}
-    d_stage = {k: torch.empty_like(d_in[k]) for k in names}
-    d_res = {"out": out, "grad_value": gv, "grad_loc": gl, "grad_weight": gw}
     h2d = sum(t.numel() * t.element_size() for t in h_in.values())
     d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+    pipe = None if args.no_e2e else HostMsdaPipeline(shapes, starts, HEADS, DH, Nq, POINTS, N_SIDE, tdt, dev)
 
     def e2e_step():
-        for k in names:
-            d_stage[k].copy_(h_in[k], non_blocking=True)
-        fwd(d_stage, cs)
-        bwd(d_stage, cs)
-        for k, t in d_res.items():
-            h_out[k].copy_(t, non_blocking=True)
+        pipe.run(h_in, h_out)
 
     e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 5))
     for _ in range(2 if e2e_steps else 0):

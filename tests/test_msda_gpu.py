@@ -147,3 +147,22 @@ def test_full_size_properties():
     band = slice(96 * 200, 112 * 200)
     ref = omsda.msda_forward(d["value"], *args, d["sampling_locations"][:, band], d["attention_weights"][:, band])
     assert rel_err(o1[:, band].cpu(), ref) < FP32_TOL
+
+
+def test_host_pipeline_matches_device_path():
+    """The pinned-host entry point (chunked H2D / compute / D2H pipeline) returns what the device path returns."""
+    import bevrender_b200 as bb
+    from bevrender_b200.host_pipeline import HostMsdaPipeline
+    d = make_microbench_inputs(3, seed=7, n_side=20, h=4, Dh=32, L=2, P=4)
+    out, gv, gl, gw = _run_cuda(d, torch.float32, False, False)
+    S = sum(h * w for h, w in d["spatial_shapes"])
+    pipe = HostMsdaPipeline(d["spatial_shapes"], d["level_start_index"], 4, 32, 400, 4, 20)
+    h_in = {k: d[k].contiguous().pin_memory() for k in ("value", "sampling_locations", "attention_weights", "grad_out")}
+    h_out = {"out": torch.empty(3, 400, 128).pin_memory(), "grad_value": torch.empty(3, S, 4, 32).pin_memory(),
+             "grad_loc": torch.empty(3, 400, 4, 2, 4, 2).pin_memory(), "grad_weight": torch.empty(3, 400, 4, 2, 4).pin_memory()}
+    pipe.run(h_in, h_out)
+    torch.cuda.synchronize()
+    assert torch.equal(h_out["out"], out.detach().cpu())
+    assert rel_err(h_out["grad_value"], gv.cpu()) < 1e-6          # atomics: order-dependent rounding only
+    assert torch.equal(h_out["grad_loc"], gl.cpu())
+    assert torch.equal(h_out["grad_weight"], gw.cpu())
