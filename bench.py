@@ -48,23 +48,51 @@ def peaks():
 
 
 class ClockSampler:
-    """Samples nvidia-smi SM clocks / throttle reasons while the timed region runs."""
+    """Samples SM clocks / throttle reasons through NVML while the timed region runs (nvidia-smi as fallback)."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    BITS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
     def __init__(self, index):
-        self.index, self.rows, self.stop = index, [], False
+        self.index, self.sm, self.mx, self.reasons, self.stop = index, [], [], set(), False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and vis.split(",")[index].isdigit() else index
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self.nvml = pynvml
+        except Exception:
+            self.nvml = None
         self.t = threading.Thread(target=self.run, daemon=True)
+
+    def sample(self):
+        if self.nvml is not None:
+            n = self.nvml
+            self.sm.append(n.nvmlDeviceGetClockInfo(self.h, n.NVML_CLOCK_SM))
+            self.mx.append(n.nvmlDeviceGetMaxClockInfo(self.h, n.NVML_CLOCK_SM))
+            try:
+                r = n.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = n.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            self.reasons |= {k for k, bit in self.BITS.items() if r & bit}
+            return
+        o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                            "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+        c = [v.strip() for v in o.stdout.strip().split(",")]
+        if len(c) >= 6 and c[0].isdigit():
+            self.sm.append(int(c[0]))
+            self.mx.append(int(c[1]))
+            self.reasons |= {k for k, v in zip(self.BITS, c[2:6]) if v == "Active"}
 
     def run(self):
         while not self.stop:
             try:
-                o = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                    "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                self.rows.append([c.strip() for c in o.stdout.strip().split(",")])
+                self.sample()
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.002)
 
     def __enter__(self):
         self.t.start()
@@ -75,12 +103,9 @@ class ClockSampler:
         self.t.join(timeout=6)
 
     def summary(self):
-        sm = sorted(int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit())
-        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v == "Active"})
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(sm)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(self.mx) if self.mx else None,
+                "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
 def cpu_reference_step(B_sample, dtype_name, threads):
@@ -193,7 +218,7 @@ def run_train(args):
         print(json.dumps({"metric": "train samples/s", "value": world * B / (ms * 1e-3), "unit": "samples/s",
                           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "loss": float(loss),
+                          "data": "synthetic", "loss": float(loss.detach()),
                           "config": {"workload": "config5: harness training step, bev %d, 6 layers, window 4, "
                                      "image 128x160, C=64, 2 heads, D=5" % n, "batch_per_gpu": B,
                                      "parallelism": "dp%d, flat fp32 gradient bucket (%d params, %.1f MB), 2 NCCL "
