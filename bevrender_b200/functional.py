@@ -190,3 +190,24 @@ def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None):
     if scale is None:
         scale = q.shape[1] ** -0.5
     return _RpeAttention.apply(q, k, v, rpe_table, pos, int(Hq), int(Wq), h // n_groups, scale)
+
+
+def correlate(map_tile, template, angles_rad):
+    """K5: rotation-sweep valid-mode correlation on the tcgen05 tensor cores (bf16 operands, fp32 accumulate).
+
+    map_tile (C, Hm, Wm), template (C, Ht, Wt) fp32 CUDA; angles_rad: sequence / CPU tensor of R angles.
+    Returns (R, Hm-Ht+1, Wm-Wt+1) fp32.  No reference counterpart exists.
+    """
+    _need_cuda(map_tile, template)
+    m, t = map_tile.contiguous().float(), template.contiguous().float()
+    ang = [float(a) for a in (angles_rad.tolist() if torch.is_tensor(angles_rad) else angles_rad)]
+    Cc, Hm, Wm = m.shape
+    _, Ht, Wt = t.shape
+    R = len(ang)
+    L = _lib.lib()
+    nws = L.bevr_correlate_workspace_bytes(Cc, Hm, Wm, Ht, Wt, R)
+    ws = torch.empty(max(nws, 16), dtype=torch.uint8, device=m.device)
+    out = torch.empty(R, Hm - Ht + 1, Wm - Wt + 1, dtype=torch.float32, device=m.device)
+    _lib.check(L.bevr_correlate(_ptr(m), _ptr(t), (C.c_float * R)(*ang), _ptr(out), _ptr(ws), Cc, Hm, Wm, Ht, Wt, R,
+                                _stream()), "bevr_correlate")
+    return out

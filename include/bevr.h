@@ -135,6 +135,24 @@ int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v, const floa
                       float* delta_ws, void* workspace, int BH, int h, int hpg, int Dh, int Hq,
                       int Wq, int Ns, int Rh, int Rw, float scale, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * K5  rotation-sweep correlation of a BEV template against an aerial-map tile (tcgen05 tensor cores).
+ * The reference has NO registration / correlation code: this operator is defined by
+ * oracle/correlate.py ("parity unpinned vs reference").
+ *   out[r, y, x] = sum_{c,u,v} map[c, y+u, x+v] * rot_r(tmpl)[c, u, v]      valid mode, fp32 out
+ *   map        dev  f32 (C, Hm, Wm)
+ *   tmpl       dev  f32 (C, Ht, Wt)     Wt % 16 == 0
+ *   angles_rad host f32 (R)             rot_r samples tmpl bilinearly (zeros outside) at
+ *                                       centre + R(angle_r) (v - cx, u - cy), centre = ((Wt-1)/2, (Ht-1)/2)
+ *   out        dev  f32 (R, Hm-Ht+1, Wm-Wt+1)
+ *   workspace  dev  bevr_correlate_workspace_bytes() bytes (bf16 operands: 8 shifted map copies + the
+ *                   rotated templates in UMMA core-matrix order)
+ * Operands are rounded to bf16, products accumulate in fp32 (TMEM).  R <= 128.
+ */
+size_t bevr_correlate_workspace_bytes(int C, int Hm, int Wm, int Ht, int Wt, int R);
+int bevr_correlate(const float* map, const float* tmpl, const float* angles_rad, float* out,
+                   void* workspace, int C, int Hm, int Wm, int Ht, int Wt, int R, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
