@@ -24,7 +24,7 @@
 
 namespace bevr {
 
-constexpr int CORR_ROWS = 4;       // output rows (accumulators) per CTA
+constexpr int CORR_ROWS = 4;       // max output rows (accumulators) per CTA
 constexpr int CORR_M = 128;        // output columns per CTA = UMMA M
 constexpr int CORR_XPAD = 128;     // zero columns appended to every shifted map row (A tiles over-read)
 
@@ -33,6 +33,7 @@ struct CorrArgs {
   const __nv_bfloat16* btile;  // (C, Ht, Wt/8, NP/8, 8, 8) rotated templates in UMMA K-major core-matrix order
   float* out;                  // (R, Ho, Wo)
   int C, Hm, Wmp, Ht, Wt, R, NP, Ho, Wo;
+  int rows;                    // output rows (TMEM accumulators) per CTA, <= CORR_ROWS
 };
 
 // ---- operand preparation -------------------------------------------------------------------------
@@ -115,25 +116,38 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 }
 
 // ---- main kernel ---------------------------------------------------------------------------------
+// Warp roles: warp 0 / lane 0 issues the MMAs; warps 1-3 (96 threads) stage operands with cp.async.
+// Two G stages + a (rows+1)-deep ring of B slices; full[s] (loaders -> MMA, 96 arrivals) and empty[s]
+// (tcgen05.commit -> loaders) mbarriers let the staging of map row i+1 overlap the MMAs of row i.
+constexpr int CORR_LOADERS = 96;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant__ CorrArgs a) {
   extern __shared__ __align__(128) uint8_t smem[];
   const int nblk = CORR_M / 8 + a.Wt / 8;                   // 16-byte blocks of one staged map row, per shift
-  const int g_bytes = nblk * 128;
+  const int g_bytes = (nblk * 128 + 127) & ~127;
   const int b_bytes = (a.Wt / 8) * a.NP * 16;               // one rotated-template slice B(c, u)
-  uint8_t* sG = smem;
-  uint8_t* sB = smem + ((g_bytes + 127) & ~127);
-  __shared__ __align__(8) uint64_t s_bar;
+  const int ring = a.rows + 1;
+  uint8_t* sG = smem;                                       // 2 stages
+  uint8_t* sB = smem + 2 * g_bytes;                         // `ring` slices
+  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], s_done;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5;
-  const int x0 = blockIdx.x * CORR_M, y0 = blockIdx.y * CORR_ROWS;
-  const uint32_t bar = smem_u32(&s_bar);
+  const int x0 = blockIdx.x * CORR_M, y0 = blockIdx.y * a.rows;
 
   if (tid == 0) {
-    mbar_init(bar, 1);
+    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_full[i]), CORR_LOADERS); mbar_init(smem_u32(&s_empty[i]), 1); }
+    mbar_init(smem_u32(&s_done), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 0) {   // TMEM: 4 accumulators of NP fp32 columns (<= 512 columns)
+  if (warp == 0) {   // TMEM: `rows` accumulators of NP fp32 columns (<= 512 columns)
     __syncwarp();
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::);
@@ -143,54 +157,68 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
   tc_fence_after();
   const uint32_t tmem = s_tmem;
 
-  // instruction descriptor: D = f32, A = B = bf16, K-major both, N = NP, M = 128
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.NP >> 3) << 17) | ((uint32_t)(CORR_M >> 4) << 24);
-  const int ksteps = a.Wt / 16;
-  const size_t plane = (size_t)a.C * a.Hm * a.Wmp;          // elements of one shifted copy
-  uint32_t phase = 0;
-  uint32_t started = 0;                                      // bit yy: accumulator yy has been written once
+  const int vrows = min(a.rows, a.Ho - y0);                  // valid output rows of this CTA
+  const int rows_c = vrows + a.Ht - 1;                       // map rows touched per channel
+  const int n_it = a.C * rows_c;
 
-  for (int c = 0; c < a.C; ++c) {
-    const int rows = min(CORR_ROWS, a.Ho - y0) + a.Ht - 1;   // map rows touched by this CTA's output rows
-    for (int rr = 0; rr < rows; ++rr) {
-      const int rho = y0 + rr;
-      // ---- stage G[blk][s] (16 B each) of map row rho and, if a new u enters, its B slice
-      const __nv_bfloat16* rowp = a.smap + ((size_t)c * a.Hm + rho) * a.Wmp + x0;
-      for (int i = tid; i < nblk * 8; i += 128) {
-        const int blk = i >> 3, s = i & 7;
-        reinterpret_cast<uint4*>(sG)[i] = __ldg(reinterpret_cast<const uint4*>(rowp + (size_t)s * plane + 8 * blk));
+  if (warp > 0) {
+    // ================= loaders =================
+    const int lt = tid - 32;
+    const size_t plane = (size_t)a.C * a.Hm * a.Wmp;        // elements of one shifted copy
+    int c = 0, rr = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1, k = it >> 1;
+      if (k >= 1) mbar_wait(smem_u32(&s_empty[s]), (uint32_t)(k - 1) & 1u);   // MMAs of iteration it-2 retired
+      const __nv_bfloat16* rowp = a.smap + ((size_t)c * a.Hm + (y0 + rr)) * a.Wmp + x0;
+      const uint32_t g0 = smem_u32(sG + s * g_bytes);
+      for (int i = lt; i < nblk * 8; i += CORR_LOADERS)     // G[blk][shift], 16 B each
+        cp_async16(g0 + i * 16, rowp + (size_t)(i & 7) * plane + 8 * (i >> 3));
+      if (rr < a.Ht) {                                       // a new template row u = rr enters the ring
+        const int t = c * a.Ht + rr;
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(a.btile) + (size_t)t * b_bytes;
+        const uint32_t d0 = smem_u32(sB + (size_t)(t % ring) * b_bytes);
+        for (int i = lt; i < b_bytes / 16; i += CORR_LOADERS) cp_async16(d0 + i * 16, src + (size_t)i * 16);
       }
-      if (rr < a.Ht) {
-        const uint4* src = reinterpret_cast<const uint4*>(a.btile + ((size_t)c * a.Ht + rr) * (size_t)(b_bytes / 2));
-        uint4* dst = reinterpret_cast<uint4*>(sB + (size_t)(rr % CORR_ROWS) * b_bytes);
-        for (int i = tid; i < b_bytes / 16; i += 128) dst[i] = __ldg(src + i);
-      }
-      fence_async_smem();          // generic-proxy stores -> visible to the tensor-core (async) proxy
-      __syncthreads();
-      if (tid == 0) {
-        tc_fence_after();
-        for (int yy = 0; yy < CORR_ROWS; ++yy) {
-          const int u = rr - yy;
-          if (u < 0 || u >= a.Ht || y0 + yy >= a.Ho) continue;
-          const uint32_t bbase = smem_u32(sB + (size_t)(u % CORR_ROWS) * b_bytes);
-          for (int ks = 0; ks < ksteps; ++ks) {
-            const uint64_t da = umma_desc(smem_u32(sG) + ks * 256, 128, 128);
-            const uint64_t db = umma_desc(bbase + ks * 2 * a.NP * 16, a.NP * 16, 128);
-            umma_bf16(tmem + yy * a.NP, da, db, idesc, (started >> yy) & 1u);
-            started |= 1u << yy;
-          }
-        }
-        umma_commit(bar);          // arrives when every MMA issued so far has finished reading shared memory
-      }
-      mbar_wait(bar, phase);       // single stage: the staging buffers are reused next iteration
-      phase ^= 1;
+      asm volatile("cp.async.wait_all;" ::: "memory");
+      fence_async_smem();          // generic-proxy writes -> visible to the tensor-core (async) proxy
+      mbar_arrive(smem_u32(&s_full[s]));
+      if (++rr == rows_c) { rr = 0; ++c; }
     }
+  } else if (tid == 0) {
+    // ================= MMA issuer =================
+    // instruction descriptor: D = f32, A = B = bf16, K-major both, N = NP, M = 128
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.NP >> 3) << 17) | ((uint32_t)(CORR_M >> 4) << 24);
+    const int ksteps = a.Wt / 16;
+    uint32_t started = 0;                                    // bit yy: accumulator yy has been written once
+    int c = 0, rr = 0;
+    for (int it = 0; it < n_it; ++it) {
+      const int s = it & 1, k = it >> 1;
+      mbar_wait(smem_u32(&s_full[s]), (uint32_t)k & 1u);
+      tc_fence_after();
+      const uint32_t gbase = smem_u32(sG + s * g_bytes);
+      for (int yy = 0; yy < vrows; ++yy) {
+        const int u = rr - yy;
+        if (u < 0 || u >= a.Ht) continue;
+        const uint32_t bbase = smem_u32(sB + (size_t)((c * a.Ht + u) % ring) * b_bytes);
+        for (int ks = 0; ks < ksteps; ++ks) {
+          const uint64_t da = umma_desc(gbase + ks * 256, 128, 128);
+          const uint64_t db = umma_desc(bbase + ks * 2 * a.NP * 16, a.NP * 16, 128);
+          umma_bf16(tmem + yy * a.NP, da, db, idesc, (started >> yy) & 1u);
+          started |= 1u << yy;
+        }
+      }
+      umma_commit(smem_u32(&s_empty[s]));   // arrives when the MMAs issued so far have finished reading smem
+      if (++rr == rows_c) { rr = 0; ++c; }
+    }
+    umma_commit(smem_u32(&s_done));
   }
+  __syncwarp();
+  mbar_wait(smem_u32(&s_done), 0);
 
   // ---- epilogue: TMEM -> registers -> out[r][y][x]
   tc_fence_after();
   const int m = tid;                                          // TMEM lane = output column x0 + m
-  for (int yy = 0; yy < CORR_ROWS; ++yy) {
+  for (int yy = 0; yy < vrows; ++yy) {
     const int y = y0 + yy;
     for (int n0 = 0; n0 < a.NP; n0 += 8) {
       uint32_t v[8];
@@ -199,7 +227,7 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
                    : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      if (y < a.Ho && x0 + m < a.Wo) {
+      if (x0 + m < a.Wo) {
 #pragma unroll
         for (int j = 0; j < 8; ++j)
           if (n0 + j < a.R) a.out[((size_t)(n0 + j) * a.Ho + y) * a.Wo + x0 + m] = __uint_as_float(v[j]);
@@ -220,8 +248,8 @@ static int corr_dims(int C, int Hm, int Wm, int Ht, int Wt, int R, int& NP, int&
   const int need = ((wo + CORR_M - 1) / CORR_M) * CORR_M + Wt + 8;        // furthest column an A tile reads
   Wmp = ((need > Wm + CORR_XPAD ? need : Wm + CORR_XPAD) + 7) / 8 * 8;
   const int nblk = CORR_M / 8 + Wt / 8;
-  smem = (size_t)((nblk * 128 + 127) & ~127) + (size_t)CORR_ROWS * (Wt / 8) * NP * 16;
-  BEVR_REQUIRE(smem <= 220 * 1024, "correlate: template %d wide x %d rotations needs %zu B of shared memory", Wt, R, smem);
+  smem = (size_t)2 * ((nblk * 128 + 127) & ~127) + (size_t)(CORR_ROWS + 1) * (Wt / 8) * NP * 16;
+  BEVR_REQUIRE(smem <= 225 * 1024, "correlate: template %d wide x %d rotations needs %zu B of shared memory", Wt, R, smem);
   return 0;
 }
 
@@ -257,8 +285,19 @@ extern "C" int bevr_correlate(const float* map, const float* tmpl, const float* 
   a.smap = smap; a.btile = btile; a.out = out;
   a.C = C; a.Hm = Hm; a.Wmp = Wmp; a.Ht = Ht; a.Wt = Wt; a.R = R; a.NP = NP;
   a.Ho = Hm - Ht + 1; a.Wo = Wm - Wt + 1;
+  // rows per CTA: fewer rows = more, cheaper CTAs (better wave balance on 148 SMs) but more B-slice traffic;
+  // pick the count with the smallest makespan (ceil(CTAs / 148) * rows)
+  const int xt = (a.Wo + CORR_M - 1) / CORR_M;
+  int best = CORR_ROWS;
+  long best_cost = -1;
+  for (int r = CORR_ROWS; r >= 2; --r) {
+    const long ctas = (long)xt * ((a.Ho + r - 1) / r);
+    const long cost = ((ctas + 147) / 148) * (r + 0);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = r; }
+  }
+  a.rows = best;
   cudaFuncSetAttribute(corr_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid((a.Wo + CORR_M - 1) / CORR_M, (a.Ho + CORR_ROWS - 1) / CORR_ROWS);
+  dim3 grid(xt, (a.Ho + a.rows - 1) / a.rows);
   corr_umma_kernel<<<grid, 128, smem, st>>>(a);
   return check_launch("correlate");
 }
