@@ -345,8 +345,13 @@ def main():
     peak, peak_src = peaks()
     dom = ("msda_bwd_kernel", ab_bwd, t_bwd) if t_bwd >= t_fwd else ("msda_fwd_kernel", ab_fwd, t_fwd)
     achieved = dom[1] / (dom[2] * 1e-3) / 1e9
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels at B=8 fp32, from the ncu --set full
+    # capture committed as profiles/r1_ncu_msda.md (bwd: 1.709 GB + 0.907 GB; fwd: 0.927 GB + 0.313 GB)
+    ncu_traffic = {"msda_bwd_kernel": 2.616e9, "msda_fwd_kernel": 1.240e9} if (dt == 0 and B == 8) else {}
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak, "traffic": ncu_traffic.get(dom[0]), "peak_source": peak_src,
+                "limiter": "bwd: SM->L2 request path (RED.ADD.F32x4 payload, 88% busy); fwd: L1 data-pipe wavefronts "
+                           "(one 128 B wavefront per tap, 73% busy) -- see DESIGN.md section 4",
                 "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[2],
                 "fwd": {"ms": t_fwd, "GBps": ab_fwd / (t_fwd * 1e-3) / 1e9},
                 "bwd": {"ms": t_bwd, "GBps": ab_bwd / (t_bwd * 1e-3) / 1e9,

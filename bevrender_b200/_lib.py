@@ -23,6 +23,7 @@ SIGNATURES = {
     "bevr_msda_bwd": (_i, [_p] * 11 + [_i] * 10 + [_p]),
     "bevr_msda_set_tile": (None, [_i] * 3),
     "bevr_project_points": (_i, [_p] * 6 + [_i] * 3 + [_p]),
+    "bevr_affine_warp": (_i, [_p] * 3 + [_i] * 4 + [_p]),
     "bevr_correlate_workspace_bytes": (_z, [_i] * 6),
     "bevr_correlate": (_i, [_p] * 5 + [_i] * 6 + [_p]),
     "bevr_rpe_attn_workspace_bytes": (_z, [_i] * 4),

@@ -211,3 +211,34 @@ def correlate(map_tile, template, angles_rad):
     _lib.check(L.bevr_correlate(_ptr(m), _ptr(t), (C.c_float * R)(*ang), _ptr(out), _ptr(ws), Cc, Hm, Wm, Ht, Wt, R,
                                 _stream()), "bevr_correlate")
     return out
+
+
+def affine_warp(img, theta):
+    """One batched torchvision-style affine resampling pass (bilinear, fill=0): img (B,C,H,W), theta (B,2,3)."""
+    _need_cuda(img, theta)
+    img, theta = img.contiguous().float(), theta.contiguous().float()
+    B, Cc, H, W = img.shape
+    out = torch.empty_like(img)
+    _lib.check(_lib.lib().bevr_affine_warp(_ptr(img), _ptr(theta), _ptr(out), B, Cc, H, W, _stream()), "bevr_affine_warp")
+    return out
+
+
+@torch.no_grad()
+def project_history_bev(bev, vehicle_pose):
+    """Drop-in for ``EncoderLayer.project_history_bev_feat(bev, vehicle_pose)`` (encoder.py:413-466): rotate by the
+    previous heading and translate by the ego motion, then rotate back by the current heading -- the same TWO
+    bilinear resampling passes as the reference, batched, with the matrices built on the device (no ``.item()``
+    / ``math.degrees(tensor)`` syncs).  bev (B,C,H,W); vehicle_pose (B,2,3) rows (x, y, heading) of prev / current.
+    """
+    p = vehicle_pose.to(bev.device).double()
+    prev_rot, curr_rot = p[:, 0, 2], p[:, 1, 2]
+    d = (vehicle_pose[:, 0, :2] - vehicle_pose[:, 1, :2]).to(bev.device).double()     # fp32 difference, as the reference
+    tx, ty = d[:, 0], d[:, 1]
+    # the reference converts to degrees and torchvision back to radians: keep that round trip
+    r1 = torch.deg2rad(torch.rad2deg(prev_rot))
+    r2 = torch.deg2rad(torch.rad2deg(-curr_rot))
+    c1, s1, c2, s2 = r1.cos(), r1.sin(), r2.cos(), r2.sin()
+    zero = torch.zeros_like(c1)
+    th1 = torch.stack((c1, s1, c1 * (-tx) + s1 * (-ty), -s1, c1, (-s1) * (-tx) + c1 * (-ty)), -1)
+    th2 = torch.stack((c2, s2, zero, -s2, c2, zero), -1)
+    return affine_warp(affine_warp(bev, th1.float()), th2.float())

@@ -153,6 +153,17 @@ size_t bevr_correlate_workspace_bytes(int C, int Hm, int Wm, int Ht, int Wt, int
 int bevr_correlate(const float* map, const float* tmpl, const float* angles_rad, float* out,
                    void* workspace, int C, int Hm, int Wm, int Ht, int Wt, int R, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * History-BEV ego-motion warp ("next" row f-1): one batched pass of torchvision's tensor F.affine
+ * (bilinear, fill = 0) as called twice per sample by EncoderLayer.project_history_bev_feat
+ * (encoder.py:436-453).
+ *   in, out  dev f32 (B, C, H, W), out != in
+ *   theta    dev f32 (B, 2, 3)   inverse affine matrices in centred pixel units
+ *                                (torchvision _get_inverse_affine_matrix with center = 0)
+ */
+int bevr_affine_warp(const float* in, const float* theta, float* out, int B, int C, int H, int W,
+                     void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -171,6 +171,20 @@ def make_sca(name, N, D, C, h, g, B, Hi, Wi, scale_offset_range=True, seed=0):
     print(name, "out", tuple(out.shape), "masked ref", float((ref_pts == -1).all(-1).float().mean()))
 
 
+def make_history_warp(name, B=3, C=8, N=14, seed=17):
+    """EncoderLayer.project_history_bev_feat (encoder.py:413-466) uses no attribute of self."""
+    load_reference()
+    from model.encoder import EncoderLayer
+    gen = torch.Generator().manual_seed(seed)
+    bev = torch.randn(B, C, N, N, generator=gen)
+    pose = torch.randn(B, 2, 3, generator=gen)
+    pose[..., :2] *= 2.0           # translations of a few BEV cells
+    pose[..., 2] *= 0.4            # headings in radians
+    out = EncoderLayer.project_history_bev_feat(None, bev, pose)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), bev=bev.numpy(), pose=pose.numpy(), out=out.numpy())
+    print(name, tuple(out.shape), float(out.abs().mean()))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     make_tsa("tsa_s1", N=14, C=64, h=2, g=1, k=3, s=1, B=2)
@@ -180,6 +194,7 @@ def main():
     make_sca("sca_d5", N=14, D=5, C=64, h=2, g=1, B=2, Hi=16, Wi=20)
     make_sca("sca_g2", N=12, D=4, C=64, h=4, g=2, B=1, Hi=16, Wi=20, seed=11)
     make_sca("sca_clamp", N=12, D=3, C=32, h=1, g=1, B=1, Hi=16, Wi=20, scale_offset_range=False, seed=13)
+    make_history_warp("history_warp")
     bound = {"X": 20.0, "Y": 10.0, "Z": 2.0}
     make_proj("proj_n50", 50, 5, bound, -1.0, 0.0, 0.0)
     make_proj("proj_n200", 200, 4, bound, -1.0, 0.0, 0.0)
