@@ -27,7 +27,7 @@ def test_cuda_warp_identity_and_bigger_batch():
     torch.manual_seed(0)
     bev = torch.randn(5, 16, 28, 28)
     pose = torch.zeros(5, 2, 3)
-    assert torch.equal(bb.project_history_bev(bev.cuda(), pose.cuda()).cpu(), bev)     # zero motion: exact identity
+    assert rel_err(bb.project_history_bev(bev.cuda(), pose.cuda()).cpu(), bev) < 1e-5   # zero motion: identity up to fp32 rounding of the grid
     pose = torch.randn(5, 2, 3)
     ref = ohw.project_history_bev(bev, pose)
     assert rel_err(bb.project_history_bev(bev.cuda(), pose.cuda()).cpu(), ref) < FP32_TOL
