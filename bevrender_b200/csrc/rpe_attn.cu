@@ -20,6 +20,7 @@ struct RpeArgs {
   const float *q, *k, *v, *rpe_pad, *pos, *out, *lse, *grad_out, *delta;
   float *o_out, *o_lse, *grad_q, *grad_k, *grad_v, *grad_rpe_pad, *grad_pos, *o_delta;
   int BH, h, hpg, Hq, Wq, Nq, Ns, Rh, Rw, Hp, Wp;
+  int gcopies;   // privatised copies of the padded table gradient (CTAs spread their atomics over them)
   float scale;
 };
 
@@ -83,12 +84,17 @@ __global__ void rpe_pad_kernel(const float* __restrict__ rpe, float* __restrict_
     pad[i] = (x >= 0 && x < Rw && y >= 0 && y < Rh) ? rpe[((size_t)hh * Rh + y) * Rw + x] : 0.f;
   }
 }
-__global__ void rpe_unpad_add_kernel(const float* __restrict__ gpad, float* __restrict__ grad, int h, int Rh, int Rw) {
+__global__ void rpe_unpad_add_kernel(const float* __restrict__ gpad, float* __restrict__ grad, int h, int Rh, int Rw,
+                                     int copies) {
   const int Hp = Rh + 4, Wp = Rw + 4;
   const int n = h * Rh * Rw;
+  const size_t copy_stride = (size_t)h * Hp * Wp;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const int x = i % Rw, y = (i / Rw) % Rh, hh = i / (Rw * Rh);
-    grad[i] += gpad[((size_t)hh * Hp + y + 2) * Wp + x + 2];
+    const float* src = gpad + ((size_t)hh * Hp + y + 2) * Wp + x + 2;
+    float s = 0.f;
+    for (int c = 0; c < copies; ++c) s += src[c * copy_stride];
+    grad[i] += s;
   }
 }
 
@@ -107,14 +113,14 @@ __device__ __forceinline__ void stage_transposed(float* __restrict__ dst, const 
 // slot on sm_100: the kernels of this file are FMA-issue bound).  Register operands are float2 pairs.
 template <int DH>
 __device__ __forceinline__ float dot32(const float2* reg, const float* __restrict__ srow) {
-  float2 s = make_float2(0.f, 0.f);
+  float2 s0 = make_float2(0.f, 0.f), s1 = make_float2(0.f, 0.f);     // two chains: halves the FFMA2 latency path
 #pragma unroll
   for (int c = 0; c < DH / 4; ++c) {
     const float4 kk = *reinterpret_cast<const float4*>(srow + 4 * c);
-    s = __ffma2_rn(reg[2 * c], make_float2(kk.x, kk.y), s);
-    s = __ffma2_rn(reg[2 * c + 1], make_float2(kk.z, kk.w), s);
+    s0 = __ffma2_rn(reg[2 * c], make_float2(kk.x, kk.y), s0);
+    s1 = __ffma2_rn(reg[2 * c + 1], make_float2(kk.z, kk.w), s1);
   }
-  return s.x + s.y;
+  return (s0.x + s1.x) + (s0.y + s1.y);
 }
 template <int DH>
 __device__ __forceinline__ void axpy32(float2* acc, float a, const float* __restrict__ srow) {
@@ -265,7 +271,7 @@ __global__ void __launch_bounds__(TQ) rpe_attn_bwd_dq_kernel(const __grid_consta
 }
 
 // dK, dV, dpos, drpe: thread = key column, streams Q/dO tiles
-constexpr int TKB = 128, TQB = 32;
+constexpr int TKB = 128, TQB = 64;
 
 template <int DH>
 __global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_constant__ RpeArgs a) {
@@ -276,7 +282,10 @@ __global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_cons
   const bool live = j < a.Ns;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
-  float* gtable = a.grad_rpe_pad ? a.grad_rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2 : nullptr;
+  // the table gradient is a hot spot (every (query, key) pair of a head lands on ~12k cells): spread the atomics of
+  // different CTAs over `gcopies` private copies, summed by rpe_unpad_add_kernel (-47 % backward time at N=56)
+  float* gtable = a.grad_rpe_pad ? a.grad_rpe_pad + ((size_t)((blockIdx.x + blockIdx.y) % a.gcopies) * a.h + head) * a.Hp * a.Wp +
+                                       2 * a.Wp + 2 : nullptr;
   const float* qb = a.q + (size_t)bh * DH * a.Nq;
   const float* gb = a.grad_out + (size_t)bh * DH * a.Nq;
 
@@ -364,9 +373,14 @@ static int validate(int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns, int 
 using namespace bevr;
 
 static size_t pad_floats(int h, int Rh, int Rw) { return (size_t)h * (Rh + 4) * (Rw + 4); }
+static int grad_copies(int h, int Rh, int Rw) {     // up to 16 private gradient tables within 64 MB
+  const size_t bytes = pad_floats(h, Rh, Rw) * sizeof(float);
+  size_t c = ((size_t)64 << 20) / bytes;
+  return c < 1 ? 1 : (c > 16 ? 16 : (int)c);
+}
 
 extern "C" size_t bevr_rpe_attn_workspace_bytes(int h, int Rh, int Rw, int backward) {
-  return pad_floats(h, Rh, Rw) * sizeof(float) * (backward ? 2 : 1);
+  return pad_floats(h, Rh, Rw) * sizeof(float) * (backward ? 1 + grad_copies(h, Rh, Rw) : 1);
 }
 
 extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
@@ -401,6 +415,7 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   a.q = q; a.k = k; a.v = v; a.rpe_pad = pad; a.pos = pos; a.out = out; a.lse = lse; a.grad_out = grad_out;
   a.delta = delta_ws; a.o_delta = delta_ws;
   a.grad_q = grad_q; a.grad_k = grad_k; a.grad_v = grad_v; a.grad_rpe_pad = grad_rpe ? gpad : nullptr;
+  a.gcopies = grad_copies(h, Rh, Rw);
   a.grad_pos = grad_pos;
   a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
   a.Hp = Rh + 4; a.Wp = Rw + 4;
@@ -408,7 +423,7 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   cudaStream_t st = (cudaStream_t)stream;
   rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, pad, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_bwd pad")) return rc;
-  if (grad_rpe) cudaMemsetAsync(gpad, 0, pad_floats(h, Rh, Rw) * sizeof(float), st);
+  if (grad_rpe) cudaMemsetAsync(gpad, 0, pad_floats(h, Rh, Rw) * sizeof(float) * a.gcopies, st);
   if (Dh == 32) rpe_delta_kernel<32><<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
   else rpe_delta_kernel<16><<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
   if (int rc = check_launch("rpe_attn_bwd delta")) return rc;
@@ -423,7 +438,7 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
     if (int rc = check_launch("rpe_attn_bwd dkv")) return rc;
   }
   if (grad_rpe) {
-    rpe_unpad_add_kernel<<<148, 256, 0, st>>>(gpad, grad_rpe, h, Rh, Rw);
+    rpe_unpad_add_kernel<<<148, 256, 0, st>>>(gpad, grad_rpe, h, Rh, Rw, a.gcopies);
     if (int rc = check_launch("rpe_attn_bwd unpad")) return rc;
   }
   return 0;

@@ -25,7 +25,9 @@ def timeit(fn, warm=3, iters=10):
 
 
 def main():
-    B, N, C, h, D = 8, int(os.environ.get("N", 56)), 64, 2, 5
+    env = lambda k, d: int(os.environ.get(k, d))
+    B, N, C, h, D = env("B", 8), env("N", 56), env("C", 64), env("H", 2), env("D", 5)
+    iters = env("ITERS", 10)
     torch.manual_seed(0)
     dev = "cuda"
     tsa = bb.TSADeformableAttention(N, C, h, 1, 1, 3, True, B, n_views=1).to(dev)
@@ -47,9 +49,11 @@ def main():
         if bwd:
             out.backward(go)
 
-    res = {"N": N, "B": B,
-           "tsa_fwd_ms": timeit(lambda: run_tsa(False)), "tsa_fwd_bwd_ms": timeit(run_tsa),
-           "sca_fwd_ms": timeit(lambda: run_sca(False)), "sca_fwd_bwd_ms": timeit(run_sca)}
+    w = 1 if iters < 5 else 3
+    res = {"N": N, "B": B, "C": C, "heads": h, "D": D,
+           "tsa_fwd_ms": timeit(lambda: run_tsa(False), w, iters), "tsa_fwd_bwd_ms": timeit(run_tsa, w, iters),
+           "sca_fwd_ms": timeit(lambda: run_sca(False), w, iters), "sca_fwd_bwd_ms": timeit(run_sca, w, iters),
+           "peak_mem_GB": torch.cuda.max_memory_allocated() / 1e9}
     print(json.dumps(res))
 
 
