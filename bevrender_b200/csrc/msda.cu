@@ -22,6 +22,22 @@
 //    inner loops avoid integer division and 64-bit address chains.
 #include "bevr_common.cuh"
 
+// tunables (overridable with -D for sweeps; defaults are the measured best, see profiles/r1_results.md)
+#ifndef MSDA_FWD_MINB
+#define MSDA_FWD_MINB 6
+#endif
+#ifndef MSDA_BWD_MINB
+#define MSDA_BWD_MINB 4
+#endif
+#ifndef MSDA_FWD_UNROLL
+#define MSDA_FWD_UNROLL 4
+#endif
+#ifndef MSDA_BWD_UNROLL
+#define MSDA_BWD_UNROLL 2
+#endif
+#define MSDA_STR2(x) #x
+#define MSDA_STR(x) MSDA_STR2(x)
+
 namespace bevr {
 
 struct MsdaArgs {
@@ -172,7 +188,7 @@ __device__ __forceinline__ const char* opaque(const char* p) {
 
 // ------------------------------------------------------------------ forward
 template <typename T, int NV, int LPG>
-__global__ void __launch_bounds__(256) msda_fwd_kernel(const __grid_constant__ MsdaArgs a) {
+__global__ void __launch_bounds__(256, MSDA_FWD_MINB) msda_fwd_kernel(const __grid_constant__ MsdaArgs a) {
   constexpr int GPW = 32 / LPG;                    // groups per warp
   constexpr unsigned VB = Chan<T, NV>::BYTES;
   extern __shared__ uint4 smem[];
@@ -215,7 +231,7 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const __grid_constant__ M
     float acc[NV];
 #pragma unroll
     for (int ch = 0; ch < NV; ++ch) acc[ch] = 0.f;
-#pragma unroll 4
+_Pragma(MSDA_STR(unroll MSDA_FWD_UNROLL))
     for (int p = 0; p < LP; ++p) {
       const uint4 o = s_off[p];
       const float4 w = s_w[p];
@@ -239,7 +255,7 @@ __global__ void __launch_bounds__(256) msda_fwd_kernel(const __grid_constant__ M
 
 // ------------------------------------------------------------------ backward
 template <typename T, int LPG>
-__global__ void __launch_bounds__(256) msda_bwd_kernel(const __grid_constant__ MsdaArgs a) {
+__global__ void __launch_bounds__(256, MSDA_BWD_MINB) msda_bwd_kernel(const __grid_constant__ MsdaArgs a) {
   constexpr int NV = 4;
   constexpr int GPW = 32 / LPG;
   constexpr unsigned VB = Chan<T, NV>::BYTES;
@@ -286,7 +302,7 @@ __global__ void __launch_bounds__(256) msda_bwd_kernel(const __grid_constant__ M
     const size_t li0 = item * LP;
     int l = 0, pl = 0;                                   // level of point p, tracked without division
     float sxl = unnormalize_scale(a.lvl_w[0], a.flags), syl = unnormalize_scale(a.lvl_h[0], a.flags);
-#pragma unroll 2
+_Pragma(MSDA_STR(unroll MSDA_BWD_UNROLL))
     for (int p = 0; p < LP; ++p) {
       const uint4 o = s_off[p];
       const float4 w = s_w[p];
