@@ -117,9 +117,10 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 // ---- main kernel ---------------------------------------------------------------------------------
 // Warp roles: warp 0 / lane 0 issues the MMAs; warps 1-3 (96 threads) stage operands with cp.async.
-// Two G stages + a (rows+1)-deep ring of B slices; full[s] (loaders -> MMA, 96 arrivals) and empty[s]
+// CORR_STAGES G stages + a (rows + CORR_STAGES - 1)-deep ring of B slices; full[s] (loaders -> MMA, 96 arrivals) and empty[s]
 // (tcgen05.commit -> loaders) mbarriers let the staging of map row i+1 overlap the MMAs of row i.
 constexpr int CORR_LOADERS = 96;
+constexpr int CORR_STAGES = 3;     // staged map rows in flight (loaders run up to 2 rows ahead of the MMAs)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -133,17 +134,17 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
   const int nblk = CORR_M / 8 + a.Wt / 8;                   // 16-byte blocks of one staged map row, per shift
   const int g_bytes = (nblk * 128 + 127) & ~127;
   const int b_bytes = (a.Wt / 8) * a.NP * 16;               // one rotated-template slice B(c, u)
-  const int ring = a.rows + 1;
-  uint8_t* sG = smem;                                       // 2 stages
-  uint8_t* sB = smem + 2 * g_bytes;                         // `ring` slices
-  __shared__ __align__(8) uint64_t s_full[2], s_empty[2], s_done;
+  const int ring = a.rows + CORR_STAGES - 1;
+  uint8_t* sG = smem;                                       // CORR_STAGES stages
+  uint8_t* sB = smem + CORR_STAGES * g_bytes;               // `ring` slices
+  __shared__ __align__(8) uint64_t s_full[CORR_STAGES], s_empty[CORR_STAGES], s_done;
   __shared__ uint32_t s_tmem;
 
   const int tid = threadIdx.x, warp = tid >> 5;
   const int x0 = blockIdx.x * CORR_M, y0 = blockIdx.y * a.rows;
 
   if (tid == 0) {
-    for (int i = 0; i < 2; ++i) { mbar_init(smem_u32(&s_full[i]), CORR_LOADERS); mbar_init(smem_u32(&s_empty[i]), 1); }
+    for (int i = 0; i < CORR_STAGES; ++i) { mbar_init(smem_u32(&s_full[i]), CORR_LOADERS); mbar_init(smem_u32(&s_empty[i]), 1); }
     mbar_init(smem_u32(&s_done), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -167,8 +168,8 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
     const size_t plane = (size_t)a.C * a.Hm * a.Wmp;        // elements of one shifted copy
     int c = 0, rr = 0;
     for (int it = 0; it < n_it; ++it) {
-      const int s = it & 1, k = it >> 1;
-      if (k >= 1) mbar_wait(smem_u32(&s_empty[s]), (uint32_t)(k - 1) & 1u);   // MMAs of iteration it-2 retired
+      const int s = it % CORR_STAGES, k = it / CORR_STAGES;
+      if (k >= 1) mbar_wait(smem_u32(&s_empty[s]), (uint32_t)(k - 1) & 1u);   // MMAs of iteration it-CORR_STAGES retired
       const __nv_bfloat16* rowp = a.smap + ((size_t)c * a.Hm + (y0 + rr)) * a.Wmp + x0;
       const uint32_t g0 = smem_u32(sG + s * g_bytes);
       for (int i = lt; i < nblk * 8; i += CORR_LOADERS)     // G[blk][shift], 16 B each
@@ -192,7 +193,7 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
     uint32_t started = 0;                                    // bit yy: accumulator yy has been written once
     int c = 0, rr = 0;
     for (int it = 0; it < n_it; ++it) {
-      const int s = it & 1, k = it >> 1;
+      const int s = it % CORR_STAGES, k = it / CORR_STAGES;
       mbar_wait(smem_u32(&s_full[s]), (uint32_t)k & 1u);
       tc_fence_after();
       const uint32_t gbase = smem_u32(sG + s * g_bytes);
@@ -239,17 +240,32 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512));
 }
 
-static int corr_dims(int C, int Hm, int Wm, int Ht, int Wt, int R, int& NP, int& Wmp, size_t& smem) {
+static size_t corr_smem(int Wt, int NP, int rows) {
+  const int nblk = CORR_M / 8 + Wt / 8;
+  return (size_t)CORR_STAGES * ((nblk * 128 + 127) & ~127) + (size_t)(rows + CORR_STAGES - 1) * (Wt / 8) * NP * 16;
+}
+
+static int corr_dims(int C, int Hm, int Wm, int Ht, int Wt, int R, int& NP, int& Wmp, int& rows, size_t& smem) {
   BEVR_REQUIRE(C > 0 && Hm >= Ht && Wm >= Wt && Ht > 0 && Wt > 0 && R > 0, "correlate: bad sizes");
   BEVR_REQUIRE(Wt % 16 == 0, "correlate: template width must be a multiple of 16 (UMMA K step), got %d", Wt);
   NP = (R + 15) / 16 * 16;
   BEVR_REQUIRE(NP * CORR_ROWS <= 512, "correlate: at most %d rotations per call (TMEM columns), got %d", 512 / CORR_ROWS, R);
-  const int wo = Wm - Wt + 1;
+  const int wo = Wm - Wt + 1, ho = Hm - Ht + 1;
   const int need = ((wo + CORR_M - 1) / CORR_M) * CORR_M + Wt + 8;        // furthest column an A tile reads
   Wmp = ((need > Wm + CORR_XPAD ? need : Wm + CORR_XPAD) + 7) / 8 * 8;
-  const int nblk = CORR_M / 8 + Wt / 8;
-  smem = (size_t)2 * ((nblk * 128 + 127) & ~127) + (size_t)(CORR_ROWS + 1) * (Wt / 8) * NP * 16;
-  BEVR_REQUIRE(smem <= 225 * 1024, "correlate: template %d wide x %d rotations needs %zu B of shared memory", Wt, R, smem);
+  // rows per CTA: fewer rows = more, cheaper CTAs (better wave balance on 148 SMs) but more B-slice traffic;
+  // pick the count with the smallest makespan ceil(CTAs / 148) * rows among those whose staging fits in smem
+  const int xt = (wo + CORR_M - 1) / CORR_M;
+  rows = 0;
+  long best_cost = -1;
+  for (int r = CORR_ROWS; r >= 1; --r) {
+    if (corr_smem(Wt, NP, r) > 225 * 1024) continue;
+    const long ctas = (long)xt * ((ho + r - 1) / r);
+    const long cost = ((ctas + 147) / 148) * r;
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; rows = r; }
+  }
+  BEVR_REQUIRE(rows > 0, "correlate: template %d wide x %d rotations does not fit in shared memory", Wt, R);
+  smem = corr_smem(Wt, NP, rows);
   return 0;
 }
 
@@ -258,17 +274,17 @@ static int corr_dims(int C, int Hm, int Wm, int Ht, int Wt, int R, int& NP, int&
 using namespace bevr;
 
 extern "C" size_t bevr_correlate_workspace_bytes(int C, int Hm, int Wm, int Ht, int Wt, int R) {
-  int NP, Wmp;
+  int NP, Wmp, rows;
   size_t smem;
-  if (corr_dims(C, Hm, Wm, Ht, Wt, R, NP, Wmp, smem)) return 0;
+  if (corr_dims(C, Hm, Wm, Ht, Wt, R, NP, Wmp, rows, smem)) return 0;
   return (size_t)8 * C * Hm * Wmp * 2 + (size_t)C * Ht * Wt * NP * 2 + 256;
 }
 
 extern "C" int bevr_correlate(const float* map, const float* tmpl, const float* angles_rad, float* out, void* workspace,
                               int C, int Hm, int Wm, int Ht, int Wt, int R, void* stream) {
-  int NP, Wmp;
+  int NP, Wmp, rows;
   size_t smem;
-  if (int rc = corr_dims(C, Hm, Wm, Ht, Wt, R, NP, Wmp, smem)) return rc;
+  if (int rc = corr_dims(C, Hm, Wm, Ht, Wt, R, NP, Wmp, rows, smem)) return rc;
   BEVR_REQUIRE(map && tmpl && angles_rad && out && workspace, "correlate: NULL pointer argument");
   cudaStream_t st = (cudaStream_t)stream;
   uint8_t* ws = (uint8_t*)workspace;
@@ -285,17 +301,8 @@ extern "C" int bevr_correlate(const float* map, const float* tmpl, const float* 
   a.smap = smap; a.btile = btile; a.out = out;
   a.C = C; a.Hm = Hm; a.Wmp = Wmp; a.Ht = Ht; a.Wt = Wt; a.R = R; a.NP = NP;
   a.Ho = Hm - Ht + 1; a.Wo = Wm - Wt + 1;
-  // rows per CTA: fewer rows = more, cheaper CTAs (better wave balance on 148 SMs) but more B-slice traffic;
-  // pick the count with the smallest makespan (ceil(CTAs / 148) * rows)
   const int xt = (a.Wo + CORR_M - 1) / CORR_M;
-  int best = CORR_ROWS;
-  long best_cost = -1;
-  for (int r = CORR_ROWS; r >= 2; --r) {
-    const long ctas = (long)xt * ((a.Ho + r - 1) / r);
-    const long cost = ((ctas + 147) / 148) * (r + 0);
-    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = r; }
-  }
-  a.rows = best;
+  a.rows = rows;
   cudaFuncSetAttribute(corr_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   dim3 grid(xt, (a.Ho + a.rows - 1) / a.rows);
   corr_umma_kernel<<<grid, 128, smem, st>>>(a);

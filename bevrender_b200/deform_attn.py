@@ -33,12 +33,23 @@ class LayerNormProxy(nn.Module):
         return self.norm(x.permute(0, 2, 3, 1)).permute(0, 3, 1, 2)
 
 
+class PointwiseConv2d(nn.Conv2d):
+    """1x1 convolution evaluated as a batched matmul.  Same parameter (``weight`` of shape (out, in, 1, 1)) as
+    ``nn.Conv2d(c_in, c_out, 1, bias=False)``; cuDNN picks ``wgrad2d_grouped_direct_kernel`` for the 2- / D-channel
+    outputs of the offset heads, which alone cost 1.7 ms (TSA) / 4.1 ms (SCA) per backward at N=56, B=8."""
+
+    def forward(self, x):
+        B, C, H, W = x.shape
+        w = self.weight.reshape(self.out_channels, C)
+        return torch.matmul(w, x.reshape(B, C, H * W)).reshape(B, self.out_channels, H, W)
+
+
 def _offset_net(c_in, c_mid, c_out, kernel_size, stride, pad):
     return nn.Sequential(
         nn.Conv2d(c_in, c_mid, kernel_size, stride, pad, groups=c_in),
         LayerNormProxy(c_mid),
         nn.GELU(),
-        nn.Conv2d(c_mid, c_out, 1, 1, 0, bias=False),
+        PointwiseConv2d(c_mid, c_out, 1, 1, 0, bias=False),
     )
 
 
@@ -90,15 +101,23 @@ class _DeformAttnBase(nn.Module):
         pos = raw.permute(0, 2, 3, 1) + ref
         return pos if self.scale_offset_range else pos.clamp(-1.0, +1.0)
 
+    @staticmethod
+    def _pointwise(conv, x):
+        """conv: nn.Conv2d(C_in, C_out, 1); x (B, C_in, N) -> (B, C_out, N)."""
+        w = conv.weight.reshape(conv.out_channels, conv.in_channels)
+        return torch.baddbmm(conv.bias.reshape(1, -1, 1), w.expand(x.shape[0], -1, -1), x)
+
     def _attend(self, x_grouped, pos, query):
         """gather (K1/K2) -> K/V projections -> fused RPE attention (K3) -> (B, C, Hq, Wq)."""
         if self.training and self.attn_drop_rate.p > 0:
             raise NotImplementedError("attention dropout is not fused into the sm_100a kernel; use attn_drop_rate=0")
         B, C, Hq, Wq = query.shape
         Ns = pos.shape[1] * pos.shape[2]
-        xs = grid_gather(x_grouped, pos).reshape(B, C, 1, Ns)
-        k = self.proj_k(xs).reshape(B * self.n_heads, self.n_channel_per_head, Ns)
-        v = self.proj_v(xs).reshape(B * self.n_heads, self.n_channel_per_head, Ns)
+        xs = grid_gather(x_grouped, pos).reshape(B, C, Ns)
+        # proj_k / proj_v are 1x1 convolutions over a (B, C, 1, Ns) tensor: evaluate them as batched matmuls
+        # (cuDNN selects wgrad2d_grouped_direct_kernel for this H = 1 shape: 1.7 ms (TSA) / 4.1 ms (SCA) per backward)
+        k = self._pointwise(self.proj_k, xs).reshape(B * self.n_heads, self.n_channel_per_head, Ns)
+        v = self._pointwise(self.proj_v, xs).reshape(B * self.n_heads, self.n_channel_per_head, Ns)
         q = query.reshape(B * self.n_heads, self.n_channel_per_head, Hq * Wq)
         out = rpe_attention(q, k, v, self.rpe_table, pos.reshape(-1, Ns, 2), Hq, Wq, self.n_groups, self.scale)
         return out.reshape(B, C, Hq, Wq)
