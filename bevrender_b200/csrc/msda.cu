@@ -380,7 +380,8 @@ static int g_tile_w = 0, g_tile_h = 0;
 static int fill_args(MsdaArgs& a, const int32_t* spatial_hw, const int32_t* level_start, int B, int S, int h,
                      int Dh, int Nq, int L, int P, int query_w, int dtype, int flags, int nv) {
   BEVR_REQUIRE(dtype == BEVR_F32 || dtype == BEVR_BF16, "msda: dtype must be 0 (f32) or 1 (bf16), got %d", dtype);
-  BEVR_REQUIRE(B > 0 && S > 0 && h > 0 && Dh > 0 && Nq > 0 && L > 0 && P > 0, "msda: all dimensions must be > 0");
+  BEVR_REQUIRE(B >= 0 && S > 0 && h > 0 && Dh > 0 && Nq >= 0 && L > 0 && P > 0,
+               "msda: S, h, Dh, L, P must be > 0 and B, Nq >= 0");
   BEVR_REQUIRE(L <= BEVR_MAX_LEVELS, "msda: at most %d levels (got %d)", BEVR_MAX_LEVELS, L);
   const int vec = dtype == BEVR_F32 ? 4 : 8;
   BEVR_REQUIRE(Dh % vec == 0, "msda: Dh*sizeof(dtype) must be a multiple of 16 bytes (Dh=%d)", Dh);
@@ -403,7 +404,7 @@ static int fill_args(MsdaArgs& a, const int32_t* spatial_hw, const int32_t* leve
     BEVR_REQUIRE(Nq % query_w == 0, "msda: query_w=%d does not divide Nq=%d", query_w, Nq);
     a.qw = query_w; a.qh = Nq / query_w;
   } else {
-    a.qw = Nq; a.qh = 1; tw = tw * th; th = 1;
+    a.qw = Nq > 0 ? Nq : 1; a.qh = 1; tw = tw * th; th = 1;
   }
   a.tw_shift = 0;
   while ((2 << a.tw_shift) <= tw) ++a.tw_shift;       // round the tile width down to a power of two
@@ -470,6 +471,7 @@ extern "C" int bevr_msda_fwd(const void* value, const int32_t* spatial_hw, const
   if (int rc = fill_args(a, spatial_hw, level_start, B, S, h, Dh, Nq, L, P, query_w, dtype, flags,
                          dtype == BEVR_F32 ? 4 : 8))
     return rc;
+  if (B == 0 || Nq == 0) return 0;                 // empty batch / empty query list: nothing to do
   BEVR_REQUIRE(value && sampling_loc && out, "msda_fwd: value / sampling_loc / out must not be NULL");
   a.value = value; a.loc = sampling_loc; a.ref = ref_points; a.weight = attn_weight; a.out = out;
   cudaStream_t st = (cudaStream_t)stream;
@@ -487,6 +489,12 @@ extern "C" int bevr_msda_bwd(const void* value, const int32_t* spatial_hw, const
                              int dtype, int flags, void* stream) {
   MsdaArgs a = {};
   if (int rc = fill_args(a, spatial_hw, level_start, B, S, h, Dh, Nq, L, P, query_w, dtype, flags, 4)) return rc;
+  if (B == 0) return 0;
+  if (Nq == 0) {                                   // no queries: grad_value is all zeros, nothing else to write
+    if (grad_value && !(flags & BEVR_ACCUMULATE))
+      cudaMemsetAsync(grad_value, 0, (size_t)B * S * h * Dh * (dtype == BEVR_F32 ? 4 : 2), (cudaStream_t)stream);
+    return 0;
+  }
   BEVR_REQUIRE(value && sampling_loc && grad_out, "msda_bwd: value / sampling_loc / grad_out must not be NULL");
   BEVR_REQUIRE(!(attn_weight == nullptr && grad_weight != nullptr), "msda_bwd: grad_weight without attn_weight");
   BEVR_REQUIRE(!(dtype == BEVR_BF16 && grad_value && !workspace), "msda_bwd: bf16 grad_value needs the fp32 workspace");

@@ -45,6 +45,20 @@ def test_argument_validation_returns_negative_and_message():
     assert rc < 0
 
 
+def test_empty_inputs_are_a_successful_no_op():
+    """Empty batch / empty query list: the entry points return 0 without touching the device."""
+    from bevrender_b200 import _lib
+    L = _lib.lib()
+    hw = (C.c_int32 * 2)(4, 4)
+    st = (C.c_int32 * 1)(0)
+    assert L.bevr_msda_fwd(None, hw, st, None, None, None, None, 0, 16, 1, 4, 8, 1, 1, 0, 0, 0, None) == 0
+    assert L.bevr_msda_fwd(None, hw, st, None, None, None, None, 2, 16, 1, 4, 0, 1, 1, 0, 0, 0, None) == 0
+    assert L.bevr_msda_bwd(None, hw, st, None, None, None, None, None, None, None, None, 0, 16, 1, 4, 8, 1, 1, 0, 0, 0,
+                           None) == 0
+    assert L.bevr_project_points(None, (C.c_float * 16)(), (C.c_float * 9)(), None, None, None, 0, 160, 128, None) < 0
+    assert L.bevr_msda_fwd(None, hw, st, None, None, None, None, -1, 16, 1, 4, 8, 1, 1, 0, 0, 0, None) < 0
+
+
 def test_operators_refuse_cpu_tensors():
     import torch
     import bevrender_b200 as bb

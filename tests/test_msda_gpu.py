@@ -166,3 +166,15 @@ def test_host_pipeline_matches_device_path():
     assert rel_err(h_out["grad_value"], gv.cpu()) < 1e-6          # atomics: order-dependent rounding only
     assert torch.equal(h_out["grad_loc"], gl.cpu())
     assert torch.equal(h_out["grad_weight"], gw.cpu())
+
+
+def test_empty_query_list():
+    """Nq = 0: forward returns an empty tensor, backward a zero grad_value (no kernel launch)."""
+    import bevrender_b200 as bb
+    v = torch.randn(2, 16, 2, 8, device="cuda", requires_grad=True)
+    loc = torch.zeros(2, 0, 2, 1, 3, 2, device="cuda")
+    w = torch.zeros(2, 0, 2, 1, 3, device="cuda")
+    out = bb.ms_deform_attn(v, [(4, 4)], [0], loc, w)
+    assert out.shape == (2, 0, 16)
+    out.sum().backward()
+    assert v.grad is not None and float(v.grad.abs().max()) == 0.0
