@@ -108,6 +108,21 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this process to the CPUs NVML reports as closest to its GPU BEFORE any pinned host buffer is
+    allocated, so the staging pages of the e2e leg are first-touched on the GPU's own NUMA node (with 8 ranks
+    on one box, remote-socket staging memory halves the aggregate PCIe throughput)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        phys = int(vis.split(",")[local_rank]) if vis and vis.split(",")[local_rank].isdigit() else local_rank
+        pynvml.nvmlDeviceSetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(phys))
+        return sorted(os.sched_getaffinity(0))
+    except Exception:
+        return None
+
+
 def cpu_reference_step(B_sample, dtype_name, threads):
     """One fwd+bwd of the CPU oracle (grid_sample-based MSDA, the construction the reference uses)
     on B_sample samples of the config-2 workload.  Returns seconds."""
@@ -253,6 +268,7 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    cpus = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -381,7 +397,8 @@ def main():
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / max(e2e_steps, 1)
     e2e = None if args.no_e2e else {"value": world * B * Nq / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
-           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps}
+           "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+           "host_cpus_bound": None if cpus is None else len(cpus)}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

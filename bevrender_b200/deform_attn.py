@@ -96,8 +96,11 @@ class _DeformAttnBase(nn.Module):
         """raw (B*g, 2, Hk, Wk) offset-net output in (y, x); ref (B*g, Hk, Wk, 2)."""
         Hk, Wk = raw.shape[-2:]
         if self.scale_offset_range:
-            rng = torch.tensor([1.0 / (Hk - 1.0), 1.0 / (Wk - 1.0)], device=raw.device).reshape(1, 2, 1, 1)
-            raw = raw.tanh().mul(rng).mul(self.offset_range_factor)
+            key = ("rng", Hk, Wk, str(raw.device))
+            if key not in self._grids:           # built once per shape: no per-forward host->device copy
+                self._grids[key] = torch.tensor([1.0 / (Hk - 1.0), 1.0 / (Wk - 1.0)],
+                                                device=raw.device).reshape(1, 2, 1, 1)
+            raw = raw.tanh().mul(self._grids[key]).mul(self.offset_range_factor)
         pos = raw.permute(0, 2, 3, 1) + ref
         return pos if self.scale_offset_range else pos.clamp(-1.0, +1.0)
 
