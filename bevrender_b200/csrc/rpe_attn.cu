@@ -135,10 +135,22 @@ __device__ __forceinline__ void axpy32(float2* acc, float a, const float* __rest
 __device__ __forceinline__ float& lane_elem(float2* r, int c) { return (c & 1) ? r[c >> 1].y : r[c >> 1].x; }
 
 // ------------------------------------------------------------------ forward (thread = query row)
-constexpr int TQ = 128, TK = 64, CH = 16;
+#ifndef K3_TQ
+#define K3_TQ 128
+#endif
+#ifndef K3_CH
+#define K3_CH 8
+#endif
+#ifndef K3_FWD_MINB
+#define K3_FWD_MINB 4
+#endif
+#ifndef K3_DQ_MINB
+#define K3_DQ_MINB 3
+#endif
+constexpr int TQ = K3_TQ, TK = 64, CH = K3_CH;
 
 template <int DH>
-__global__ void __launch_bounds__(TQ) rpe_attn_fwd_kernel(const __grid_constant__ RpeArgs a) {
+__global__ void __launch_bounds__(TQ, K3_FWD_MINB) rpe_attn_fwd_kernel(const __grid_constant__ RpeArgs a) {
   __shared__ __align__(16) float sK[TK * PAD];
   __shared__ __align__(16) float sV[TK * PAD];
   __shared__ float2 sPos[TK];
@@ -220,7 +232,7 @@ __global__ void __launch_bounds__(256) rpe_delta_kernel(const __grid_constant__ 
 
 // dQ: thread = query row, streams K/V tiles
 template <int DH>
-__global__ void __launch_bounds__(TQ) rpe_attn_bwd_dq_kernel(const __grid_constant__ RpeArgs a) {
+__global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const __grid_constant__ RpeArgs a) {
   __shared__ __align__(16) float sK[TK * PAD];
   __shared__ __align__(16) float sV[TK * PAD];
   __shared__ float2 sPos[TK];
@@ -271,10 +283,16 @@ __global__ void __launch_bounds__(TQ) rpe_attn_bwd_dq_kernel(const __grid_consta
 }
 
 // dK, dV, dpos, drpe: thread = key column, streams Q/dO tiles
-constexpr int TKB = 128, TQB = 64;
+#ifndef K3_TQB
+#define K3_TQB 128
+#endif
+#ifndef K3_DKV_MINB
+#define K3_DKV_MINB 1
+#endif
+constexpr int TKB = 128, TQB = K3_TQB;
 
 template <int DH>
-__global__ void __launch_bounds__(TKB) rpe_attn_bwd_dkv_kernel(const __grid_constant__ RpeArgs a) {
+__global__ void __launch_bounds__(TKB, K3_DKV_MINB) rpe_attn_bwd_dkv_kernel(const __grid_constant__ RpeArgs a) {
   __shared__ __align__(16) float sQ[TQB * PAD];
   __shared__ __align__(16) float sG[TQB * PAD];
   __shared__ float4 sRow[TQB];    // qy, qx, lse, delta
