@@ -185,6 +185,37 @@ def make_history_warp(name, B=3, C=8, N=14, seed=17):
     print(name, tuple(out.shape), float(out.abs().mean()))
 
 
+def make_encoder_layer(name, N=14, C=64, h=2, D=5, B=2, Hi=16, Wi=20, seed=23):
+    """One reference EncoderLayer (encoder.py:243-411) in train mode with prev_bev: LPU -> TSA -> MLP -> LPU -> SCA -> MLP."""
+    _, _, Projector, _ = load_reference()
+    from model.encoder import EncoderLayer
+    torch.manual_seed(seed)
+    gen = torch.Generator().manual_seed(seed + 1)
+    T, K = camera_setup()
+    proj = Projector(imu_to_rgb={0: [T]}, K={0: [K]}, vehicle_type_code=0, img_width=Wi * 4, img_height=Hi * 4,
+                     ori_img_width=640, ori_img_height=512, device="cpu")
+    layer = EncoderLayer(bev_bound={"X": 20.0, "Y": 10.0, "Z": 2.0}, bev2cmr_projector=proj, n_views=1, bev_feat_shape=N,
+                         bev_depth_dim=D, z_shift=-1.0, dim_embed=C, expansion=2, stage_idx=0, n_groups=1, n_heads=h,
+                         stride=1, kernel_size=3, batch_size=B, scale_offset_range=True, drop_path_rate=0.0)
+    stress_init(layer.temporal_self_attn.temporal_deform_attn, gen, 8.0)
+    stress_init(layer.spatial_cross_attn.spatial_deform_attn, gen, 4.0)
+    layer.train()
+    q = torch.randn(B, C, N, N, generator=gen).requires_grad_(True)
+    img = torch.randn(B, C, Hi, Wi, generator=gen).requires_grad_(True)
+    prev = torch.randn(B, C, N, N, generator=gen)
+    go = torch.randn(B, C, N, N, generator=gen)
+    out, _ = layer(q, img, prev, torch.zeros(B, 2, 3), torch.tensor(0), {}, False)
+    out.backward(go)
+    ref_pts = torch.stack(layer.spatial_cross_attn.points_2d_dict[0], 0)           # (V, 2, N/2, N, D)
+    d = dict(cfg=np.array([N, C, h, D, B, Hi, Wi]), query=q.detach().numpy(), img=img.detach().numpy(), prev=prev.numpy(),
+             grad_out=go.numpy(), out=out.detach().numpy(), g_query=q.grad.numpy(), g_img=img.grad.numpy(),
+             ref_points=ref_pts.numpy())
+    d.update(np_state(layer))
+    d.update(np_grads(layer))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **d)
+    print(name, tuple(out.shape), float(out.abs().max()))
+
+
 def main():
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     make_tsa("tsa_s1", N=14, C=64, h=2, g=1, k=3, s=1, B=2)
@@ -195,6 +226,7 @@ def main():
     make_sca("sca_g2", N=12, D=4, C=64, h=4, g=2, B=1, Hi=16, Wi=20, seed=11)
     make_sca("sca_clamp", N=12, D=3, C=32, h=1, g=1, B=1, Hi=16, Wi=20, scale_offset_range=False, seed=13)
     make_history_warp("history_warp")
+    make_encoder_layer("encoder_layer")
     bound = {"X": 20.0, "Y": 10.0, "Z": 2.0}
     make_proj("proj_n50", 50, 5, bound, -1.0, 0.0, 0.0)
     make_proj("proj_n200", 200, 4, bound, -1.0, 0.0, 0.0)
