@@ -242,3 +242,22 @@ def project_history_bev(bev, vehicle_pose):
     th1 = torch.stack((c1, s1, c1 * (-tx) + s1 * (-ty), -s1, c1, (-s1) * (-tx) + c1 * (-ty)), -1)
     th2 = torch.stack((c2, s2, zero, -s2, c2, zero), -1)
     return affine_warp(affine_warp(bev, th1.float()), th2.float())
+
+
+@torch.no_grad()
+def retrieval_recall(camera_embed, map_embed, ks=(1, 5, 10)):
+    """Recall@k of the retrieval metric ("next" row f-4; Trainer.get_recall, train.py:551-572), on the device.
+
+    dist = 2 - 2 * X @ Y^T (a plain cuBLAS GEMM in fp32); for every column k the rank of the true match is the
+    number of rows with dist[:, k] < dist[k, k]; recall@i = 100 * mean(rank < i).  The reference evaluates this
+    with numpy and an O(11 * N) Python loop on the host.
+    """
+    _need_cuda(camera_embed, map_embed)
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False            # ranks are discontinuous in dist: keep fp32 products
+    try:
+        dist = 2.0 - 2.0 * (camera_embed.float() @ map_embed.float().T)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+    rank = (dist < dist.diagonal()[None, :]).sum(0)
+    return tuple(float((rank < k).float().mean() * 100) for k in ks)
