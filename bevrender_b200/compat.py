@@ -40,13 +40,19 @@ def ensure_timm_stub():
     sys.modules.update({"timm": timm, "timm.models": models, "timm.models.layers": layers})
 
 
-def install(projector=True):
+def install(projector=True, wrappers=False):
+    """``wrappers=True`` additionally rebinds ``model.encoder.{SpatialCrossAttn, TemporalSelfAttn}`` to the versions
+    that cache the projected reference points on the device (no per-forward upload / ``.item()`` sync)."""
     from . import BEV2CameraProjector, SCADeformableAttention, TSADeformableAttention
     ensure_timm_stub()
     tsa = importlib.import_module("model.TSA")
     sca = importlib.import_module("model.SCA")
     tsa.TSADeformableAttention = TSADeformableAttention
     sca.SCADeformableAttention = SCADeformableAttention
+    if wrappers:
+        from . import SpatialCrossAttn, TemporalSelfAttn
+        enc = importlib.import_module("model.encoder")
+        enc.SpatialCrossAttn, enc.TemporalSelfAttn = SpatialCrossAttn, TemporalSelfAttn
     if projector:
         try:
             top = importlib.import_module("model.bevrender")

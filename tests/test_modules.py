@@ -121,3 +121,41 @@ def test_projector_dropin_matches_reference():
     assert np.array_equal(K, g["K"])                               # caller's intrinsics untouched
     assert np.array_equal(uv.cpu().numpy().view(np.uint32), g["uv"].view(np.uint32))
     assert np.array_equal(proj.last_mask[0].cpu().numpy(), g["mask"])
+
+
+def test_wrapper_points_and_keys_match_reference():
+    """wrappers.SpatialCrossAttn.sample_3d_points reproduces the reference's pillar points bit for bit and the wrapper
+    state_dict keys equal the reference's (spatial_cross_attn.* / temporal_self_attn.* of the EncoderLayer golden)."""
+    import types
+    import numpy as np
+    import bevrender_b200 as bb
+    g, _, _ = load_golden("proj_n50")
+    stub = types.SimpleNamespace(bev_bound=dict(zip("XYZ", [float(v) for v in g["bound"]])), bev_feat_shape=50,
+                                 bev_depth_dim=5, z_shift=float(g["z_shift"]))
+    assert np.array_equal(bb.SpatialCrossAttn.sample_3d_points(stub).numpy(), g["points"])
+    _, p, _ = load_golden("encoder_layer")
+    tsa = bb.TemporalSelfAttn(14, 64, 2, 1, 1, 3, 2, True, n_views=1)
+    want = {k[len("temporal_self_attn."):] for k in p if k.startswith("temporal_self_attn.")}
+    assert set(tsa.state_dict()) == want
+
+
+@pytest.mark.gpu
+def test_spatial_cross_attn_wrapper_matches_module():
+    import bevrender_b200 as bb
+    g, p, _ = load_golden("encoder_layer")
+    N, C, h, D, B, Hi, Wi = [int(v) for v in g["cfg"]]
+    from bevrender_b200.harness import default_camera
+    T, K = default_camera()
+    proj = bb.BEV2CameraProjector({0: [T]}, {0: [K]}, 0, Wi * 4, Hi * 4, 640, 512)
+    w = bb.SpatialCrossAttn({"X": 20.0, "Y": 10.0, "Z": 2.0}, proj, N, D, -1.0, C, h, 1, 1, 3, B, True, n_views=1)
+    w.load_state_dict({k[len("spatial_cross_attn."):]: v for k, v in p.items() if k.startswith("spatial_cross_attn.")})
+    w = w.cuda()
+    q = torch.from_numpy(g["query"]).cuda()
+    img = torch.from_numpy(g["img"]).cuda()
+    out, _ = w(q, img, torch.tensor(0), {}, False)
+    ref_pts = torch.from_numpy(g["ref_points"]).cuda()
+    V, _, hh, ww, dd = ref_pts.shape
+    r = ref_pts.permute(0, 2, 3, 4, 1).reshape(1, V, hh, ww * dd, 2).expand(B, -1, -1, -1, -1)
+    assert torch.equal(w._reference_points(torch.tensor(0), q.device, B), r)       # K4 == reference projection, bit-exact
+    exp, _ = w.spatial_deform_attn(img.reshape(B, 1, C, Hi, Wi), q, r, {}, False)
+    assert torch.equal(out, exp)
