@@ -19,7 +19,7 @@ def test_recall_matches_oracle():
     rng = np.random.default_rng(0)
     maps = rng.standard_normal((200, 512)).astype(np.float32)
     maps /= np.linalg.norm(maps, axis=1, keepdims=True)
-    cam = maps + 0.08 * rng.standard_normal(maps.shape).astype(np.float32)
+    cam = maps + 0.5 * rng.standard_normal(maps.shape).astype(np.float32)
     cam /= np.linalg.norm(cam, axis=1, keepdims=True)
     ref = orec.get_recall(cam, maps)
     got = bb.retrieval_recall(torch.from_numpy(cam).cuda(), torch.from_numpy(maps).cuda())
