@@ -117,10 +117,10 @@ __device__ __forceinline__ void umma_commit(uint32_t bar) {
 
 // ---- main kernel ---------------------------------------------------------------------------------
 // Warp roles: warp 0 / lane 0 issues the MMAs; warps 1-3 (96 threads) stage operands with cp.async.
-// CORR_STAGES G stages + a (rows + CORR_STAGES - 1)-deep ring of B slices; full[s] (loaders -> MMA, 96 arrivals) and empty[s]
+// CORR_STAGES G stages + a (rows + CORR_STAGES - 1)-deep, K-chunk-interleaved ring of B slices; full[s] (loaders -> MMA, 96 arrivals) and empty[s]
 // (tcgen05.commit -> loaders) mbarriers let the staging of map row i+1 overlap the MMAs of row i.
 constexpr int CORR_LOADERS = 96;
-constexpr int CORR_STAGES = 3;     // staged map rows in flight (loaders run up to 2 rows ahead of the MMAs)
+constexpr int CORR_STAGES = 2;     // staged map rows in flight (a deeper pipeline measured no gain)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -175,10 +175,16 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
       for (int i = lt; i < nblk * 8; i += CORR_LOADERS)     // G[blk][shift], 16 B each
         cp_async16(g0 + i * 16, rowp + (size_t)(i & 7) * plane + 8 * (i >> 3));
       if (rr < a.Ht) {                                       // a new template row u = rr enters the ring
+        // slice t goes to ring position q(t) = -t mod ring (positions DEscend with u, so the slices of output rows
+        // y, y+1, y+2 -- u, u-1, u-2 -- are consecutive), interleaved by K chunk: [k8][position][NP rows x 16 B]
         const int t = c * a.Ht + rr;
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.btile) + (size_t)t * b_bytes;
-        const uint32_t d0 = smem_u32(sB + (size_t)(t % ring) * b_bytes);
-        for (int i = lt; i < b_bytes / 16; i += CORR_LOADERS) cp_async16(d0 + i * 16, src + (size_t)i * 16);
+        const int q = (ring - t % ring) % ring;
+        const uint32_t d0 = smem_u32(sB) + q * a.NP * 16;
+        for (int i = lt; i < b_bytes / 16; i += CORR_LOADERS) {
+          const int k8 = i / a.NP, r = i - k8 * a.NP;
+          cp_async16(d0 + (k8 * ring * a.NP + r) * 16, src + (size_t)i * 16);
+        }
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
       fence_async_smem();          // generic-proxy writes -> visible to the tensor-core (async) proxy
@@ -187,9 +193,13 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
     }
   } else if (tid == 0) {
     // ================= MMA issuer =================
-    // instruction descriptor: D = f32, A = B = bf16, K-major both, N = NP, M = 128
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.NP >> 3) << 17) | ((uint32_t)(CORR_M >> 4) << 24);
+    // instruction descriptor: D = f32, A = B = bf16, K-major both, M = 128, N = n
+    auto idesc_n = [](int n) {
+      return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(CORR_M >> 4) << 24);
+    };
     const int ksteps = a.Wt / 16;
+    const uint32_t lbo = (uint32_t)(ring * a.NP * 16);       // K-chunk stride of the interleaved B ring
+    const uint32_t bring = smem_u32(sB);
     uint32_t started = 0;                                    // bit yy: accumulator yy has been written once
     int c = 0, rr = 0;
     for (int it = 0; it < n_it; ++it) {
@@ -197,15 +207,30 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
       mbar_wait(smem_u32(&s_full[s]), (uint32_t)k & 1u);
       tc_fence_after();
       const uint32_t gbase = smem_u32(sG + s * g_bytes);
-      for (int yy = 0; yy < vrows; ++yy) {
-        const int u = rr - yy;
-        if (u < 0 || u >= a.Ht) continue;
-        const uint32_t bbase = smem_u32(sB + (size_t)((c * a.Ht + u) % ring) * b_bytes);
+      // output rows fed by this map row: yy in [ya, yb] <-> template rows u = rr - yy (descending), whose slices
+      // sit at consecutive ring positions.  One MMA per K step covers ALL of them (N = rows * NP): the measured
+      // cost of an MMA is ~75 + 0.53 N cycles, so merging the rows amortises the fixed part (A-operand fetch).
+      const int ya = max(0, rr - (a.Ht - 1)), yb = min(vrows - 1, rr);
+      const int nwin = yb - ya + 1;
+      const uint32_t need = ((1u << nwin) - 1u) << ya;
+      if ((started & need) != need) {
+        // start-up (first rows of channel 0): accumulators not initialised yet -> one MMA per row, overwrite first
+        for (int yy = ya; yy <= yb; ++yy) {
+          const int q = (ring - (c * a.Ht + rr - yy) % ring) % ring;
+          for (int ks = 0; ks < ksteps; ++ks) {
+            umma_bf16(tmem + yy * a.NP, umma_desc(gbase + ks * 256, 128, 128),
+                      umma_desc(bring + q * a.NP * 16 + ks * 2 * lbo, lbo, 128), idesc_n(a.NP), (started >> yy) & 1u);
+            started |= 1u << yy;
+          }
+        }
+      } else {
+        const int q = (ring - (c * a.Ht + rr - ya) % ring) % ring;      // position of the slice of row ya
+        const int n1 = min(nwin, ring - q), n2 = nwin - n1;             // the window may wrap around the ring once
         for (int ks = 0; ks < ksteps; ++ks) {
           const uint64_t da = umma_desc(gbase + ks * 256, 128, 128);
-          const uint64_t db = umma_desc(bbase + ks * 2 * a.NP * 16, a.NP * 16, 128);
-          umma_bf16(tmem + yy * a.NP, da, db, idesc, (started >> yy) & 1u);
-          started |= 1u << yy;
+          umma_bf16(tmem + ya * a.NP, da, umma_desc(bring + q * a.NP * 16 + ks * 2 * lbo, lbo, 128), idesc_n(n1 * a.NP), 1u);
+          if (n2 > 0)
+            umma_bf16(tmem + (ya + n1) * a.NP, da, umma_desc(bring + ks * 2 * lbo, lbo, 128), idesc_n(n2 * a.NP), 1u);
         }
       }
       umma_commit(smem_u32(&s_empty[s]));   // arrives when the MMAs issued so far have finished reading smem
@@ -259,7 +284,7 @@ static int corr_dims(int C, int Hm, int Wm, int Ht, int Wt, int R, int& NP, int&
   rows = 0;
   long best_cost = -1;
   for (int r = CORR_ROWS; r >= 1; --r) {
-    if (corr_smem(Wt, NP, r) > 225 * 1024) continue;
+    if (corr_smem(Wt, NP, r) > 225 * 1024 || (r > 1 && r * NP > 256)) continue;   // merged MMA: N = r * NP <= 256
     const long ctas = (long)xt * ((ho + r - 1) / r);
     const long cost = ((ctas + 147) / 148) * r;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; rows = r; }
