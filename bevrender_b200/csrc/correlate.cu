@@ -181,9 +181,17 @@ __global__ void __launch_bounds__(128, 1) corr_umma_kernel(const __grid_constant
         const uint8_t* src = reinterpret_cast<const uint8_t*>(a.btile) + (size_t)t * b_bytes;
         const int q = (ring - t % ring) % ring;
         const uint32_t d0 = smem_u32(sB) + q * a.NP * 16;
-        for (int i = lt; i < b_bytes / 16; i += CORR_LOADERS) {
-          const int k8 = i / a.NP, r = i - k8 * a.NP;
-          cp_async16(d0 + (k8 * ring * a.NP + r) * 16, src + (size_t)i * 16);
+        if (lt < 8) {
+          // eight threads move the slice with 1-D bulk copies (TMA engine, async proxy): Wt/8 runs of NP*16 B,
+          // completing on full[s] through its transaction count -- no LDGSTS traffic, no proxy fence for B.
+          // (the phase cannot complete early: the 96 loader arrivals are still pending)
+          const uint32_t bar = smem_u32(&s_full[s]);
+          if (lt == 0)
+            asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"((uint32_t)b_bytes) : "memory");
+          const uint32_t run = (uint32_t)a.NP * 16;
+          for (int k8 = lt; k8 < a.Wt / 8; k8 += 8)
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                         ::"r"(d0 + k8 * ring * run), "l"(src + (size_t)k8 * run), "r"(run), "r"(bar) : "memory");
         }
       }
       asm volatile("cp.async.wait_all;" ::: "memory");
