@@ -18,7 +18,7 @@ Differences from the reference, all deliberate:
 import torch
 from torch import nn
 
-from .functional import grid_gather, rpe_attention
+from .functional import grid_gather, offset_head, rpe_attention
 
 
 class LayerNormProxy(nn.Module):
@@ -92,6 +92,15 @@ class _DeformAttnBase(nn.Module):
             self._grids[key] = torch.stack((gy, gx), -1)
         return self._grids[key][None].expand(B * self.n_groups, -1, -1, -1)
 
+    def _positions(self, net, xq, ref, interleave):
+        """Offset network -> sampling positions (B*g, Hk, Wk, 2) in (y, x): the depthwise convolution stays cuDNN,
+        everything after it (LayerNorm, GELU, 1x1 conv, tanh * range * factor or clamp, + reference and the two
+        rearranges) is the fused offset-head kernel (row f-2).  ``net`` is the reference-shaped nn.Sequential."""
+        ln = net[1].norm
+        return offset_head(net[0](xq), ln.weight, ln.bias, net[3].weight, ref, interleave=interleave,
+                           scaled=bool(self.scale_offset_range),
+                           factor=self.offset_range_factor if self.scale_offset_range else 1.0, eps=ln.eps)
+
     def _scaled_positions(self, raw, ref):
         """raw (B*g, 2, Hk, Wk) offset-net output in (y, x); ref (B*g, Hk, Wk, 2)."""
         Hk, Wk = raw.shape[-2:]
@@ -149,9 +158,11 @@ class TSADeformableAttention(_DeformAttnBase):
             x = query
         B, C, H, W = x.shape
         g, Cg = self.n_groups, self.n_channel_per_group
-        raw = self.conv_offset(query.reshape(B * g, Cg, H, W))
-        Hk, Wk = raw.shape[-2:]
-        pos = self._scaled_positions(raw, self._get_normalized_grid(Hk, Wk, B, x.device))
+        pad = self.kernel_size // 2 if self.kernel_size != self.stride else 0
+        Hk = (H + 2 * pad - self.kernel_size) // self.stride + 1
+        Wk = (W + 2 * pad - self.kernel_size) // self.stride + 1
+        pos = self._positions(self.conv_offset, query.reshape(B * g, Cg, H, W),
+                              self._get_normalized_grid(Hk, Wk, 1, x.device)[:1], interleave=False)
         out = self._attend(x.reshape(B * g, Cg, H, W), pos, query)
         return self.proj_drop_rate(self.proj_out(out)), wandb_log_dict
 
@@ -189,9 +200,7 @@ class SCADeformableAttention(_DeformAttnBase):
         ref = reference_points[:, 0].flip(-1)                         # (x, y) -> (y, x)
         if g > 1:
             ref = ref.repeat_interleave(g, 0)
-        raw = self.conv_offset_m0(query.reshape(B * g, Cg, Hq, Wq))   # (B*g, D, Hq, Wq)
-        # "(b g) d (h n) w -> (b g) n h (w d)", n = 2: even query rows carry y-, odd rows x-offsets
-        raw = raw.reshape(B * g, D, Hq // 2, 2, Wq).permute(0, 3, 2, 4, 1).reshape(B * g, 2, Hq // 2, Wq * D)
-        pos = self._scaled_positions(raw, ref)
+        # "(b g) d (h n) w -> (b g) n h (w d)", n = 2: even query rows carry y-, odd rows x-offsets (interleave=True)
+        pos = self._positions(self.conv_offset_m0, query.reshape(B * g, Cg, Hq, Wq), ref, interleave=True)
         out = self._attend(x[:, 0].reshape(B * g, Cg, Hi, Wi), pos, query)
         return self.proj_drop_rate(self.proj_out(out)), wandb_log_dict

@@ -192,6 +192,65 @@ def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None):
     return _RpeAttention.apply(q, k, v, rpe_table, pos, int(Hq), int(Wq), h // n_groups, scale)
 
 
+class _OffsetHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, y, ln_w, ln_b, w1, ref, interleave, scaled, factor, eps):
+        _need_cuda(y, ln_w, ln_b, w1, ref)
+        y, ref = y.contiguous().float(), ref.contiguous().float()
+        ln_w, ln_b = ln_w.contiguous().float(), ln_b.contiguous().float()
+        Bg, Cm, H, W = y.shape
+        O = w1.shape[0]
+        w1 = w1.contiguous().float()
+        Hk, Wk = (H // 2, W * O) if interleave else (H, W)
+        if tuple(ref.shape[1:]) != (Hk, Wk, 2) or ref.shape[0] not in (1, Bg):
+            raise ValueError(f"offset_head: ref must be ({Bg} or 1, {Hk}, {Wk}, 2), got {tuple(ref.shape)}")
+        stride = 0 if ref.shape[0] == 1 else Hk * Wk * 2
+        pos = torch.empty(Bg, Hk, Wk, 2, dtype=torch.float32, device=y.device)
+        stats = torch.empty(Bg * H * W, 2, dtype=torch.float32, device=y.device)
+        _lib.check(_lib.lib().bevr_offset_head_fwd(_ptr(y), _ptr(ln_w), _ptr(ln_b), _ptr(w1), _ptr(ref), stride,
+                                                   _ptr(pos), _ptr(stats), Bg, Cm, H, W, O, int(interleave), int(scaled),
+                                                   float(factor), float(eps), _stream()), "bevr_offset_head_fwd")
+        ctx.save_for_backward(y, ln_w, ln_b, w1, ref, stats)
+        ctx.meta = (stride, int(interleave), int(scaled), float(factor), float(eps))
+        return pos
+
+    @staticmethod
+    def backward(ctx, grad_pos):
+        y, ln_w, ln_b, w1, ref, stats = ctx.saved_tensors
+        stride, interleave, scaled, factor, eps = ctx.meta
+        Bg, Cm, H, W = y.shape
+        O = w1.shape[0]
+        need = ctx.needs_input_grad
+        grad_pos = grad_pos.contiguous().float()
+        gy = torch.empty_like(y) if need[0] else None
+        gw = torch.zeros_like(ln_w) if need[1] else None
+        gb = torch.zeros_like(ln_b) if need[2] else None
+        g1 = torch.zeros_like(w1) if need[3] else None
+        _lib.check(_lib.lib().bevr_offset_head_bwd(_ptr(y), _ptr(ln_w), _ptr(ln_b), _ptr(w1), _ptr(ref), stride,
+                                                   _ptr(stats), _ptr(grad_pos), _ptr(gy), _ptr(gw), _ptr(gb), _ptr(g1),
+                                                   Bg, Cm, H, W, O, interleave, scaled, factor, eps, _stream()),
+                   "bevr_offset_head_bwd")
+        gr = None
+        if need[4]:      # pos = f(raw) + ref (scaled) or clamp(raw + ref): the reference points are never trained
+            raise NotImplementedError("offset_head: gradient w.r.t. the reference points is not provided")
+        return gy, gw, gb, g1, gr, None, None, None, None
+
+
+def offset_head(y, ln_weight, ln_bias, w1, ref, interleave=False, scaled=True, factor=0.5, eps=1e-5):
+    """Fused tail of the offset network ("next" row f-2): LayerNorm over channels -> GELU -> 1x1 conv (no bias) ->
+    ``tanh * (1/(Hk-1), 1/(Wk-1)) * factor`` (or clamp to [-1, 1] when ``scaled`` is False) -> ``+ ref``.
+
+    y (B*g, Cm, H, W): output of the depthwise convolution; w1 (O, Cm[, 1, 1]); ref (B*g or 1, Hk, Wk, 2) in (y, x).
+    ``interleave=False`` (TSA): O = 2, pos[b, y, x, :] = (y, x).  ``interleave=True`` (SCA): the reference's
+    "(b g) d (h n) w -> (b g) n h (w d)" split, pos (B*g, H/2, W*O, 2).  Returns the sampling positions (y, x).
+    Replaces conv_offset[1:] + TSA_deform_attn.py:158-196 / SCA_deform_attn.py:219-277.
+    """
+    if ref.dim() == 3:
+        ref = ref[None]
+    w1 = w1.reshape(w1.shape[0], -1)          # (O, Cm, 1, 1) conv weight -> (O, Cm); autograd undoes the view
+    return _OffsetHead.apply(y, ln_weight, ln_bias, w1, ref, bool(interleave), bool(scaled), float(factor), float(eps))
+
+
 def correlate(map_tile, template, angles_rad):
     """K5: rotation-sweep valid-mode correlation on the tcgen05 tensor cores (bf16 operands, fp32 accumulate).
 

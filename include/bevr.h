@@ -164,6 +164,32 @@ int bevr_correlate(const float* map, const float* tmpl, const float* angles_rad,
 int bevr_affine_warp(const float* in, const float* theta, float* out, int B, int C, int H, int W,
                      void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Offset head ("next" row f-2): LayerNorm over channels -> GELU -> 1x1 conv (no bias) -> tanh * range * factor
+ * (or clamp) -> + reference, i.e. conv_offset[1:] and the position arithmetic of
+ * TSA_deform_attn.py:54-68,158-196 / SCA_deform_attn.py:56-77,219-277 (LayerNormProxy: model_utils.py:51-59),
+ * fused into one kernel per direction.  Input is the output of the offset network's depthwise convolution.
+ *   y          dev f32 (Bg, Cm, H, W)       NCHW
+ *   ln_weight, ln_bias dev f32 (Cm); w1 dev f32 (O, Cm)
+ *   ref        dev f32 (Bg or 1, Hk, Wk, 2) in (y, x); ref_batch_stride = Hk*Wk*2, or 0 to broadcast one grid
+ *   pos        dev f32 (Bg, Hk, Wk, 2)      sampling positions in (y, x)
+ *   stats      dev f32 (Bg*H*W, 2)          per-pixel mean / rstd, written by fwd, read by bwd
+ *   interleave 0: O == 2, (Hk, Wk) = (H, W), pos[b, y, x, o]                                  (TSA)
+ *              1: (Hk, Wk) = (H/2, W*O), pos[b, y>>1, x*O + o, y&1]  "(h n) w -> n h (w d)"   (SCA)
+ *   scaled     1: tanh(raw) * (1/(Hk-1), 1/(Wk-1)) * factor + ref;  0: clamp(raw + ref, -1, 1)
+ * Backward: grad_y is overwritten; grad_ln_weight / grad_ln_bias / grad_w1 are ACCUMULATED into (caller
+ * zero-fills).  Any of the four may be NULL.  O <= 8.
+ */
+int bevr_offset_head_fwd(const float* y, const float* ln_weight, const float* ln_bias, const float* w1,
+                         const float* ref, long long ref_batch_stride, float* pos, float* stats, int Bg,
+                         int Cm, int H, int W, int O, int interleave, int scaled, float factor, float eps,
+                         void* stream);
+int bevr_offset_head_bwd(const float* y, const float* ln_weight, const float* ln_bias, const float* w1,
+                         const float* ref, long long ref_batch_stride, const float* stats,
+                         const float* grad_pos, float* grad_y, float* grad_ln_weight, float* grad_ln_bias,
+                         float* grad_w1, int Bg, int Cm, int H, int W, int O, int interleave, int scaled,
+                         float factor, float eps, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

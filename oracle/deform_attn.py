@@ -23,16 +23,31 @@ def normalized_grid(H, W, dtype=torch.float32, device="cpu"):
     return torch.stack((gy, gx), -1)
 
 
-def offset_network(p, prefix, x, kernel_size, stride):
-    """depthwise conv -> LayerNorm over channels -> GELU -> 1x1 (no bias).
-    TSA_deform_attn.py:54-68, SCA_deform_attn.py:56-77, model_utils.py:51-59."""
-    w0 = p[prefix + ".0.weight"]
+def offset_head(y, ln_w, ln_b, w1, ref, interleave, scaled, factor):
+    """Tail of the offset network after its depthwise convolution, up to the sampling positions:
+    LayerNorm over channels -> GELU -> 1x1 (no bias) -> [rearrange] -> tanh * range * factor (or clamp) -> + ref.
+    y (B*g, Cm, H, W); w1 (O, Cm, 1, 1); ref broadcastable to (B*g, Hk, Wk, 2) in (y, x).
+    TSA_deform_attn.py:54-68,158-196; SCA_deform_attn.py:56-77,219-277; model_utils.py:51-59."""
+    z = y.permute(0, 2, 3, 1)
+    z = F.layer_norm(z, (z.shape[-1],), ln_w, ln_b)
+    off = F.conv2d(F.gelu(z.permute(0, 3, 1, 2)), w1.reshape(w1.shape[0], -1, 1, 1))
+    if interleave:   # "(b g) d (h n) w -> (b g) n h (w d)", n=2: even query rows -> y, odd rows -> x
+        Bg, D, Hq, Wq = off.shape
+        off = off.reshape(Bg, D, Hq // 2, 2, Wq).permute(0, 3, 2, 4, 1).reshape(Bg, 2, Hq // 2, Wq * D)
+    Hk, Wk = off.shape[-2:]
+    if scaled:
+        rng = torch.tensor([1.0 / (Hk - 1.0), 1.0 / (Wk - 1.0)], device=y.device).reshape(1, 2, 1, 1)
+        off = off.tanh().mul(rng).mul(factor)
+    pos = off.permute(0, 2, 3, 1) + ref
+    return pos if scaled else pos.clamp(-1.0, 1.0)
+
+
+def offset_positions(p, prefix, x, ref, kernel_size, stride, interleave, scaled, factor):
+    """depthwise conv (TSA_deform_attn.py:55-63, SCA_deform_attn.py:57-66) -> offset_head."""
     pad = kernel_size // 2 if kernel_size != stride else 0
-    y = F.conv2d(x, w0, p[prefix + ".0.bias"], stride=stride, padding=pad, groups=x.shape[1])
-    y = y.permute(0, 2, 3, 1)
-    y = F.layer_norm(y, (y.shape[-1],), p[prefix + ".1.norm.weight"], p[prefix + ".1.norm.bias"])
-    y = F.gelu(y.permute(0, 3, 1, 2))
-    return F.conv2d(y, p[prefix + ".3.weight"])
+    y = F.conv2d(x, p[prefix + ".0.weight"], p[prefix + ".0.bias"], stride=stride, padding=pad, groups=x.shape[1])
+    return offset_head(y, p[prefix + ".1.norm.weight"], p[prefix + ".1.norm.bias"], p[prefix + ".3.weight"], ref,
+                       interleave, scaled, factor)
 
 
 def rpe_bias_dense(rpe_table, pos, Hq, Wq, n_groups):
@@ -90,14 +105,10 @@ def tsa_forward(p, x, query, n_heads, n_groups, kernel_size, stride, scale_offse
         x = query.clone()
     B, C, H, W = x.shape
     Cg = C // n_groups
-    off = offset_network(p, "conv_offset", query.reshape(B * n_groups, Cg, H, W), kernel_size, stride)
-    Hk, Wk = off.shape[-2:]
-    if scale_offset_range:
-        rng = torch.tensor([1.0 / (Hk - 1.0), 1.0 / (Wk - 1.0)]).reshape(1, 2, 1, 1)
-        off = off.tanh().mul(rng).mul(0.5)
-    pos = off.permute(0, 2, 3, 1) + normalized_grid(Hk, Wk)[None]
-    if not scale_offset_range:
-        pos = pos.clamp(-1.0, 1.0)
+    pad = kernel_size // 2 if kernel_size != stride else 0
+    Hk, Wk = (H + 2 * pad - kernel_size) // stride + 1, (W + 2 * pad - kernel_size) // stride + 1
+    pos = offset_positions(p, "conv_offset", query.reshape(B * n_groups, Cg, H, W), normalized_grid(Hk, Wk)[None],
+                           kernel_size, stride, False, scale_offset_range, 0.5)
     xs = F.grid_sample(x.reshape(B * n_groups, Cg, H, W), pos.flip(-1), mode="bilinear",
                        align_corners=True).reshape(B, C, 1, Hk * Wk)
     out = _attend(p, xs, query, pos.reshape(B * n_groups, Hk * Wk, 2), n_heads, n_groups, H, W)
@@ -113,17 +124,9 @@ def sca_forward(p, x, query, reference_points, n_heads, n_groups, bev_depth_dim,
     Cg = C // n_groups
     Hi, Wi = x.shape[-2:]
     ref = reference_points[:, 0].flip(-1).repeat_interleave(n_groups, 0)          # (y,x)
-    off = offset_network(p, "conv_offset_m0", query.reshape(B * n_groups, Cg, Hq, Wq), 1, 1)
-    # "(b g) d (h n) w -> (b g) n h (w d)", n=2: even query rows -> y, odd rows -> x
-    off = off.reshape(B * n_groups, D, Hq // 2, 2, Wq).permute(0, 3, 2, 4, 1)
-    off = off.reshape(B * n_groups, 2, Hq // 2, Wq * D)
-    Hk, Wk = off.shape[-2:]
-    if scale_offset_range:
-        rng = torch.tensor([1.0 / (Hk - 1.0), 1.0 / (Wk - 1.0)]).reshape(1, 2, 1, 1)
-        off = off.tanh().mul(rng).mul(5.0)
-    pos = off.permute(0, 2, 3, 1) + ref
-    if not scale_offset_range:
-        pos = pos.clamp(-1.0, 1.0)
+    pos = offset_positions(p, "conv_offset_m0", query.reshape(B * n_groups, Cg, Hq, Wq), ref, 1, 1, True,
+                           scale_offset_range, 5.0)
+    Hk, Wk = pos.shape[1:3]
     xs = F.grid_sample(x[:, 0].reshape(B * n_groups, Cg, Hi, Wi), pos.flip(-1), mode="bilinear",
                        align_corners=True).reshape(B, C, 1, Hk * Wk)
     out = _attend(p, xs, query, pos.reshape(B * n_groups, Hk * Wk, 2), n_heads, n_groups, Hq, Wq)
