@@ -21,6 +21,10 @@ struct RpeArgs {
   float *o_out, *o_lse, *grad_q, *grad_k, *grad_v, *grad_rpe_pad, *grad_pos, *o_delta;
   int BH, h, hpg, Hq, Wq, Nq, Ns, Rh, Rw, Hp, Wp;
   int gcopies;   // privatised copies of the padded table gradient (CTAs spread their atomics over them)
+  // work splitting (blockIdx.z): the reference-native shapes are small (B*h*Nq = 50 k query rows = 11 warps per SM),
+  // so every kernel also cuts its STREAMED dimension into `split` ranges of `tiles_per_split` tiles.
+  int split, tiles_per_split;
+  float *part_o, *part_ml;   // forward partials: (split, BH, DH, Nq) unnormalised outputs, (split, BH, 2, Nq) max / sum
   float scale;
 };
 
@@ -171,8 +175,9 @@ __global__ void __launch_bounds__(TQ, K3_FWD_MINB) rpe_attn_fwd_kernel(const __g
   const int iy = i / a.Wq, ixq = i - iy * a.Wq;
   const float qy = grid_coord(iy, a.Hq), qx = grid_coord(ixq, a.Wq);
   float m = -INFINITY, l = 0.f;
+  const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
 
-  for (int j0 = 0; j0 < a.Ns; j0 += TK) {
+  for (int j0 = jbeg; j0 < jend; j0 += TK) {
     __syncthreads();
     stage_transposed<TK, DH>(sK, kb, a.Ns, j0, 1.f);
     stage_transposed<TK, DH>(sV, vb, a.Ns, j0, 1.f);
@@ -207,12 +212,42 @@ __global__ void __launch_bounds__(TQ, K3_FWD_MINB) rpe_attn_fwd_kernel(const __g
       m = mn;
     }
   }
-  if (live) {
+  if (!live) return;
+  if (a.split == 1) {
     const float inv = 1.f / l;
 #pragma unroll
     for (int c = 0; c < DH; ++c) a.o_out[((size_t)bh * DH + c) * a.Nq + i] = lane_elem(o, c) * inv;
     a.o_lse[(size_t)bh * a.Nq + i] = m + logf(l);
+  } else {      // partial (unnormalised) result of this key range; rpe_combine_kernel merges the ranges
+    const size_t pz = (size_t)blockIdx.z * a.BH + bh;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) a.part_o[(pz * DH + c) * a.Nq + i] = lane_elem(o, c);
+    a.part_ml[(pz * 2 + 0) * a.Nq + i] = m;
+    a.part_ml[(pz * 2 + 1) * a.Nq + i] = l;
   }
+}
+
+// merge the key ranges of the split forward: out = sum_z o_z e^{m_z - m} / sum_z l_z e^{m_z - m}
+template <int DH>
+__global__ void __launch_bounds__(128) rpe_combine_kernel(const __grid_constant__ RpeArgs a) {
+  const int bh = blockIdx.y, i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= a.Nq) return;
+  float m = -INFINITY;
+  for (int z = 0; z < a.split; ++z) m = fmaxf(m, __ldg(a.part_ml + (((size_t)z * a.BH + bh) * 2) * a.Nq + i));
+  float l = 0.f, o[DH];
+#pragma unroll
+  for (int c = 0; c < DH; ++c) o[c] = 0.f;
+  for (int z = 0; z < a.split; ++z) {
+    const size_t pz = (size_t)z * a.BH + bh;
+    const float w = __expf(__ldg(a.part_ml + (pz * 2) * a.Nq + i) - m);     // empty range: e^{-inf} = 0
+    l = fmaf(__ldg(a.part_ml + (pz * 2 + 1) * a.Nq + i), w, l);
+#pragma unroll
+    for (int c = 0; c < DH; ++c) o[c] = fmaf(__ldg(a.part_o + (pz * DH + c) * a.Nq + i), w, o[c]);
+  }
+  const float inv = 1.f / l;
+#pragma unroll
+  for (int c = 0; c < DH; ++c) a.o_out[((size_t)bh * DH + c) * a.Nq + i] = o[c] * inv;
+  a.o_lse[(size_t)bh * a.Nq + i] = m + logf(l);
 }
 
 // ------------------------------------------------------------------ backward
@@ -257,7 +292,8 @@ __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const _
   const int iy = i / a.Wq, ixq = i - iy * a.Wq;
   const float qy = grid_coord(iy, a.Hq), qx = grid_coord(ixq, a.Wq);
 
-  for (int j0 = 0; j0 < a.Ns; j0 += TK) {
+  const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
+  for (int j0 = jbeg; j0 < jend; j0 += TK) {
     __syncthreads();
     stage_transposed<TK, DH>(sK, kb, a.Ns, j0, 1.f);
     stage_transposed<TK, DH>(sV, vb, a.Ns, j0, 1.f);
@@ -278,7 +314,11 @@ __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const _
   }
   if (live) {
 #pragma unroll
-    for (int c = 0; c < DH; ++c) a.grad_q[((size_t)bh * DH + c) * a.Nq + i] = lane_elem(dq, c) * a.scale;
+    for (int c = 0; c < DH; ++c) {
+      float* dst = a.grad_q + ((size_t)bh * DH + c) * a.Nq + i;
+      if (a.split == 1) *dst = lane_elem(dq, c) * a.scale;
+      else atomicAdd(dst, lane_elem(dq, c) * a.scale);      // key ranges add into the zero-filled gradient
+    }
   }
 }
 
@@ -320,7 +360,8 @@ __global__ void __launch_bounds__(TKB, K3_DKV_MINB) rpe_attn_bwd_dkv_kernel(cons
   float giy = 0.f, gix = 0.f;
   const bool want_bias_grad = (a.grad_rpe_pad != nullptr) || (a.grad_pos != nullptr);
 
-  for (int i0 = 0; i0 < a.Nq; i0 += TQB) {
+  const int ibeg = blockIdx.z * a.tiles_per_split * TQB, iend = min(a.Nq, ibeg + a.tiles_per_split * TQB);
+  for (int i0 = ibeg; i0 < iend; i0 += TQB) {
     __syncthreads();
     stage_transposed<TQB, DH>(sQ, qb, a.Nq, i0, a.scale);
     stage_transposed<TQB, DH>(sG, gb, a.Nq, i0, 1.f);
@@ -365,8 +406,13 @@ __global__ void __launch_bounds__(TKB, K3_DKV_MINB) rpe_attn_bwd_dkv_kernel(cons
 #pragma unroll
     for (int c = 0; c < DH; ++c) {
       const size_t idx = ((size_t)bh * DH + c) * a.Ns + j;
-      if (a.grad_k) a.grad_k[idx] = lane_elem(dk, c);    // sQ already carries `scale`
-      if (a.grad_v) a.grad_v[idx] = lane_elem(dv, c);
+      if (a.split == 1) {
+        if (a.grad_k) a.grad_k[idx] = lane_elem(dk, c);    // sQ already carries `scale`
+        if (a.grad_v) a.grad_v[idx] = lane_elem(dv, c);
+      } else {                                              // query ranges add into the zero-filled gradients
+        if (a.grad_k) atomicAdd(a.grad_k + idx, lane_elem(dk, c));
+        if (a.grad_v) atomicAdd(a.grad_v + idx, lane_elem(dv, c));
+      }
     }
     if (a.grad_pos) {
       // table coord = (Rx-1) * ((q - pos)/4 + 1/2)  ->  d coord / d pos = -(Rx-1)/4
@@ -397,8 +443,30 @@ static int grad_copies(int h, int Rh, int Rw) {     // up to 16 private gradient
   return c < 1 ? 1 : (c > 16 ? 16 : (int)c);
 }
 
-extern "C" size_t bevr_rpe_attn_workspace_bytes(int h, int Rh, int Rw, int backward) {
-  return pad_floats(h, Rh, Rw) * sizeof(float) * (backward ? 1 + grad_copies(h, Rh, Rw) : 1);
+// Split of a kernel's streamed dimension (n_tiles tiles) so that about 3.5 waves of CTAs exist: `base` CTAs without
+// splitting, `per_sm` CTAs resident per SM (register-limited: 4 forward, 3 dQ, 2 dK/dV).  Returns the number of ranges
+// and sets tiles_per_split.  Deterministic in the shapes, so the workspace query and the launch agree.
+static int pick_split(long long base, int per_sm, int n_tiles, int* tiles_per_split) {
+  long long want = (7ll * 148 * per_sm / 2 + base - 1) / base;
+  if (want > 8) want = 8;
+  if (want > n_tiles) want = n_tiles;
+  if (want < 1) want = 1;
+  const int tps = (n_tiles + (int)want - 1) / (int)want;
+  *tiles_per_split = tps;
+  return (n_tiles + tps - 1) / tps;
+}
+static int fwd_split(int BH, int Nq, int Ns, int* tps) {
+  return pick_split((long long)((Nq + TQ - 1) / TQ) * BH, K3_FWD_MINB, (Ns + TK - 1) / TK, tps);
+}
+
+extern "C" size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward) {
+  size_t n = pad_floats(h, Rh, Rw) * (backward ? 1 + grad_copies(h, Rh, Rw) : 1);
+  if (!backward) {
+    int tps;
+    const int ks = fwd_split(BH, Nq, Ns, &tps);
+    if (ks > 1) n += (size_t)ks * BH * (Dh + 2) * Nq;
+  }
+  return n * sizeof(float);
 }
 
 extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
@@ -411,12 +479,23 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
   a.Hp = Rh + 4; a.Wp = Rw + 4;
   a.scale = scale;
-  rpe_pad_kernel<<<148, 256, 0, (cudaStream_t)stream>>>(rpe, (float*)workspace, h, Rh, Rw);
+  a.split = fwd_split(BH, a.Nq, Ns, &a.tiles_per_split);
+  a.part_o = (float*)workspace + pad_floats(h, Rh, Rw);
+  a.part_ml = a.part_o + (size_t)a.split * BH * Dh * a.Nq;
+  cudaStream_t st = (cudaStream_t)stream;
+  rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, (float*)workspace, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_fwd pad")) return rc;
-  dim3 grid((a.Nq + TQ - 1) / TQ, BH);
-  if (Dh == 32) rpe_attn_fwd_kernel<32><<<grid, TQ, 0, (cudaStream_t)stream>>>(a);
-  else rpe_attn_fwd_kernel<16><<<grid, TQ, 0, (cudaStream_t)stream>>>(a);
-  return check_launch("rpe_attn_fwd");
+  dim3 grid((a.Nq + TQ - 1) / TQ, BH, a.split);
+  if (Dh == 32) rpe_attn_fwd_kernel<32><<<grid, TQ, 0, st>>>(a);
+  else rpe_attn_fwd_kernel<16><<<grid, TQ, 0, st>>>(a);
+  if (int rc = check_launch("rpe_attn_fwd")) return rc;
+  if (a.split > 1) {
+    dim3 cgrid((a.Nq + 127) / 128, BH);
+    if (Dh == 32) rpe_combine_kernel<32><<<cgrid, 128, 0, st>>>(a);
+    else rpe_combine_kernel<16><<<cgrid, 128, 0, st>>>(a);
+    return check_launch("rpe_attn_fwd combine");
+  }
+  return 0;
 }
 
 extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
@@ -446,13 +525,22 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   else rpe_delta_kernel<16><<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
   if (int rc = check_launch("rpe_attn_bwd delta")) return rc;
   if (grad_q) {
-    if (Dh == 32) rpe_attn_bwd_dq_kernel<32><<<dim3((a.Nq + TQ - 1) / TQ, BH), TQ, 0, st>>>(a);
-    else rpe_attn_bwd_dq_kernel<16><<<dim3((a.Nq + TQ - 1) / TQ, BH), TQ, 0, st>>>(a);
+    const int nqt = (a.Nq + TQ - 1) / TQ;
+    a.split = pick_split((long long)nqt * BH, K3_DQ_MINB, (Ns + TK - 1) / TK, &a.tiles_per_split);
+    if (a.split > 1) cudaMemsetAsync(grad_q, 0, (size_t)BH * Dh * a.Nq * sizeof(float), st);
+    if (Dh == 32) rpe_attn_bwd_dq_kernel<32><<<dim3(nqt, BH, a.split), TQ, 0, st>>>(a);
+    else rpe_attn_bwd_dq_kernel<16><<<dim3(nqt, BH, a.split), TQ, 0, st>>>(a);
     if (int rc = check_launch("rpe_attn_bwd dq")) return rc;
   }
   if (grad_k || grad_v || grad_rpe || grad_pos) {
-    if (Dh == 32) rpe_attn_bwd_dkv_kernel<32><<<dim3((Ns + TKB - 1) / TKB, BH), TKB, 0, st>>>(a);
-    else rpe_attn_bwd_dkv_kernel<16><<<dim3((Ns + TKB - 1) / TKB, BH), TKB, 0, st>>>(a);
+    const int nkt = (Ns + TKB - 1) / TKB;
+    a.split = pick_split((long long)nkt * BH, 2, (a.Nq + TQB - 1) / TQB, &a.tiles_per_split);
+    if (a.split > 1) {
+      if (grad_k) cudaMemsetAsync(grad_k, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
+      if (grad_v) cudaMemsetAsync(grad_v, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
+    }
+    if (Dh == 32) rpe_attn_bwd_dkv_kernel<32><<<dim3(nkt, BH, a.split), TKB, 0, st>>>(a);
+    else rpe_attn_bwd_dkv_kernel<16><<<dim3(nkt, BH, a.split), TKB, 0, st>>>(a);
     if (int rc = check_launch("rpe_attn_bwd dkv")) return rc;
   }
   if (grad_rpe) {

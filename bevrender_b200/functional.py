@@ -148,7 +148,7 @@ class _RpeAttention(torch.autograd.Function):
         h, Rh, Rw = rpe.shape
         out = torch.empty_like(q)
         lse = torch.empty(BH, Nq, dtype=torch.float32, device=q.device)
-        ws = torch.empty(_lib.lib().bevr_rpe_attn_workspace_bytes(h, Rh, Rw, 0), dtype=torch.uint8, device=q.device)
+        ws = torch.empty(_lib.lib().bevr_rpe_attn_workspace_bytes(BH, h, Dh, Nq, Ns, Rh, Rw, 0), dtype=torch.uint8, device=q.device)
         _lib.check(_lib.lib().bevr_rpe_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
                                                 _ptr(ws), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, float(scale), _stream()),
                    "bevr_rpe_attn_fwd")
@@ -171,7 +171,7 @@ class _RpeAttention(torch.autograd.Function):
         gr = torch.zeros_like(rpe) if need[3] else None
         gp = torch.zeros_like(pos) if need[4] else None
         delta = torch.empty_like(lse)
-        ws = torch.empty(_lib.lib().bevr_rpe_attn_workspace_bytes(h, Rh, Rw, 1), dtype=torch.uint8, device=q.device)
+        ws = torch.empty(_lib.lib().bevr_rpe_attn_workspace_bytes(BH, h, Dh, Nq, Ns, Rh, Rw, 1), dtype=torch.uint8, device=q.device)
         _lib.check(_lib.lib().bevr_rpe_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
                                                 _ptr(grad_out), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(gr), _ptr(gp),
                                                 _ptr(delta), _ptr(ws), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, scale,

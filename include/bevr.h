@@ -115,11 +115,11 @@ int bevr_project_points(const float* points, const float* cam_T, const float* K,
  *   out      dev f32 (BH, Dh, Nq)
  *   lse      dev f32 (BH, Nq)         log-sum-exp per row (saved for backward)
  *   hpg      heads per group (head bh uses pos[bh / hpg], table rpe[bh % h])
- *   workspace dev, bevr_rpe_attn_workspace_bytes(h, Rh, Rw, backward) bytes: holds the zero-padded
+ *   workspace dev, bevr_rpe_attn_workspace_bytes(BH, h, Dh, Nq, Ns, Rh, Rw, backward) bytes: holds the zero-padded
  *            copy of the table the kernels sample (and, for backward, its padded gradient)
  * Requires Dh == 32 (the reference uses 32 channels per head everywhere, encoder.py:23-39) or Dh == 16.
  */
-size_t bevr_rpe_attn_workspace_bytes(int h, int Rh, int Rw, int backward);
+size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward);
 int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe,
                       const float* pos, float* out, float* lse, void* workspace, int BH, int h,
                       int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw, float scale,
