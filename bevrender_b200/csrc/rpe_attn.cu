@@ -153,28 +153,78 @@ __device__ __forceinline__ float& lane_elem(float2* r, int c) { return (c & 1) ?
 #endif
 constexpr int TQ = K3_TQ, TK = 64, CH = K3_CH;
 
+// K3_R query rows per thread (rows i and i + TQ/R of the CTA's tile): with R = 2 every broadcast LDS.128 of a K / V row
+// feeds two rows, which halves the shared-memory wavefronts per (query, key) pair -- the forward's binding pipe.
+#ifndef K3_R
+#define K3_R 1
+#endif
+#ifndef K3_R2_MINB
+#define K3_R2_MINB 4
+#endif
+constexpr int RQ = K3_R;
+constexpr int FWD_MINB = RQ == 1 ? K3_FWD_MINB : K3_R2_MINB;
+
+template <int DH, int R>
+__device__ __forceinline__ void dotR(const float2 (*reg)[DH / 2], const float* __restrict__ srow, float* out) {
+  float2 s0[R], s1[R];
+#pragma unroll
+  for (int r = 0; r < R; ++r) { s0[r] = make_float2(0.f, 0.f); s1[r] = make_float2(0.f, 0.f); }
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) {
+    const float4 kk = *reinterpret_cast<const float4*>(srow + 4 * c);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      s0[r] = __ffma2_rn(reg[r][2 * c], make_float2(kk.x, kk.y), s0[r]);
+      s1[r] = __ffma2_rn(reg[r][2 * c + 1], make_float2(kk.z, kk.w), s1[r]);
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < R; ++r) out[r] = (s0[r].x + s1[r].x) + (s0[r].y + s1[r].y);
+}
+template <int DH, int R>
+__device__ __forceinline__ void axpyR(float2 (*acc)[DH / 2], const float* a, const float* __restrict__ srow) {
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) {
+    const float4 vv = *reinterpret_cast<const float4*>(srow + 4 * c);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const float2 a2 = make_float2(a[r], a[r]);
+      acc[r][2 * c] = __ffma2_rn(a2, make_float2(vv.x, vv.y), acc[r][2 * c]);
+      acc[r][2 * c + 1] = __ffma2_rn(a2, make_float2(vv.z, vv.w), acc[r][2 * c + 1]);
+    }
+  }
+}
+
 template <int DH>
-__global__ void __launch_bounds__(TQ, K3_FWD_MINB) rpe_attn_fwd_kernel(const __grid_constant__ RpeArgs a) {
+__global__ void __launch_bounds__(TQ / RQ, FWD_MINB) rpe_attn_fwd_kernel(const __grid_constant__ RpeArgs a) {
+  constexpr int R = RQ, NT = TQ / R;
   __shared__ __align__(16) float sK[TK * PAD];
   __shared__ __align__(16) float sV[TK * PAD];
   __shared__ float2 sPos[TK];
-  const int bh = blockIdx.y, i = blockIdx.x * TQ + threadIdx.x;
-  const bool live = i < a.Nq;
+  const int bh = blockIdx.y;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
   const float* kb = a.k + (size_t)bh * DH * a.Ns;
   const float* vb = a.v + (size_t)bh * DH * a.Ns;
   const float2* pb = reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns;
 
-  float2 qr[DH / 2], o[DH / 2];
+  int iq[R];
+  bool live[R];
+  float2 qr[R][DH / 2], o[R][DH / 2];
+  float qy[R], qx[R], m[R], l[R];
 #pragma unroll
-  for (int c = 0; c < DH; ++c) {
-    lane_elem(qr, c) = live ? __ldg(a.q + ((size_t)bh * DH + c) * a.Nq + i) * a.scale : 0.f;
-    lane_elem(o, c) = 0.f;
+  for (int r = 0; r < R; ++r) {
+    iq[r] = blockIdx.x * TQ + r * NT + threadIdx.x;
+    live[r] = iq[r] < a.Nq;
+#pragma unroll
+    for (int c = 0; c < DH; ++c) {
+      lane_elem(qr[r], c) = live[r] ? __ldg(a.q + ((size_t)bh * DH + c) * a.Nq + iq[r]) * a.scale : 0.f;
+      lane_elem(o[r], c) = 0.f;
+    }
+    const int iy = iq[r] / a.Wq, ixq = iq[r] - iy * a.Wq;
+    qy[r] = grid_coord(iy, a.Hq); qx[r] = grid_coord(ixq, a.Wq);
+    m[r] = -INFINITY; l[r] = 0.f;
   }
-  const int iy = i / a.Wq, ixq = i - iy * a.Wq;
-  const float qy = grid_coord(iy, a.Hq), qx = grid_coord(ixq, a.Wq);
-  float m = -INFINITY, l = 0.f;
   const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
 
   for (int j0 = jbeg; j0 < jend; j0 += TK) {
@@ -187,43 +237,63 @@ __global__ void __launch_bounds__(TQ, K3_FWD_MINB) rpe_attn_fwd_kernel(const __g
 #pragma unroll 1
     for (int jc = 0; jc < TK; jc += CH) {
       if (j0 + jc >= a.Ns) break;
-      float s[CH];
-      float mx = -INFINITY;
+      float s[R][CH];
+      float mx[R];
+#pragma unroll
+      for (int r = 0; r < R; ++r) mx[r] = -INFINITY;
 #pragma unroll
       for (int jj = 0; jj < CH; ++jj) {
         const float2 p = sPos[jc + jj];
-        const Bilin b = rpe_taps(qy, qx, p.x, p.y, a.Rh, a.Rw, a.Wp);
-        float tv[4];
-        const float sc = dot32<DH>(qr, sK + (jc + jj) * PAD) + rpe_bias(table, b, a.Wp, tv);
-        s[jj] = (j0 + jc + jj < a.Ns) ? sc : -INFINITY;
-        mx = fmaxf(mx, s[jj]);
-      }
-      const float mn = fmaxf(m, mx);
-      const float corr = __expf(m - mn);
-      l *= corr;
+        float d[R];
+        dotR<DH, R>(qr, sK + (jc + jj) * PAD, d);
 #pragma unroll
-      for (int c = 0; c < DH / 2; ++c) { o[c].x *= corr; o[c].y *= corr; }
+        for (int r = 0; r < R; ++r) {
+          const Bilin b = rpe_taps(qy[r], qx[r], p.x, p.y, a.Rh, a.Rw, a.Wp);
+          float tv[4];
+          const float sc = d[r] + rpe_bias(table, b, a.Wp, tv);
+          s[r][jj] = (j0 + jc + jj < a.Ns) ? sc : -INFINITY;
+          mx[r] = fmaxf(mx[r], s[r][jj]);
+        }
+      }
+#pragma unroll
+      for (int r = 0; r < R; ++r) {
+        const float mn = fmaxf(m[r], mx[r]);
+        const float corr = __expf(m[r] - mn);
+        l[r] *= corr;
+#pragma unroll
+        for (int c = 0; c < DH / 2; ++c) { o[r][c].x *= corr; o[r][c].y *= corr; }
+#pragma unroll
+        for (int jj = 0; jj < CH; ++jj) {
+          s[r][jj] = __expf(s[r][jj] - mn);
+          l[r] += s[r][jj];
+        }
+        m[r] = mn;
+      }
 #pragma unroll
       for (int jj = 0; jj < CH; ++jj) {
-        const float p = __expf(s[jj] - mn);
-        l += p;
-        axpy32<DH>(o, p, sV + (jc + jj) * PAD);
+        float pr[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) pr[r] = s[r][jj];
+        axpyR<DH, R>(o, pr, sV + (jc + jj) * PAD);
       }
-      m = mn;
     }
   }
-  if (!live) return;
-  if (a.split == 1) {
-    const float inv = 1.f / l;
 #pragma unroll
-    for (int c = 0; c < DH; ++c) a.o_out[((size_t)bh * DH + c) * a.Nq + i] = lane_elem(o, c) * inv;
-    a.o_lse[(size_t)bh * a.Nq + i] = m + logf(l);
-  } else {      // partial (unnormalised) result of this key range; rpe_combine_kernel merges the ranges
-    const size_t pz = (size_t)blockIdx.z * a.BH + bh;
+  for (int r = 0; r < R; ++r) {
+    if (!live[r]) continue;
+    const int i = iq[r];
+    if (a.split == 1) {
+      const float inv = 1.f / l[r];
 #pragma unroll
-    for (int c = 0; c < DH; ++c) a.part_o[(pz * DH + c) * a.Nq + i] = lane_elem(o, c);
-    a.part_ml[(pz * 2 + 0) * a.Nq + i] = m;
-    a.part_ml[(pz * 2 + 1) * a.Nq + i] = l;
+      for (int c = 0; c < DH; ++c) a.o_out[((size_t)bh * DH + c) * a.Nq + i] = lane_elem(o[r], c) * inv;
+      a.o_lse[(size_t)bh * a.Nq + i] = m[r] + logf(l[r]);
+    } else {      // partial (unnormalised) result of this key range; rpe_combine_kernel merges the ranges
+      const size_t pz = (size_t)blockIdx.z * a.BH + bh;
+#pragma unroll
+      for (int c = 0; c < DH; ++c) a.part_o[(pz * DH + c) * a.Nq + i] = lane_elem(o[r], c);
+      a.part_ml[(pz * 2 + 0) * a.Nq + i] = m[r];
+      a.part_ml[(pz * 2 + 1) * a.Nq + i] = l[r];
+    }
   }
 }
 
@@ -456,7 +526,7 @@ static int pick_split(long long base, int per_sm, int n_tiles, int* tiles_per_sp
   return (n_tiles + tps - 1) / tps;
 }
 static int fwd_split(int BH, int Nq, int Ns, int* tps) {
-  return pick_split((long long)((Nq + TQ - 1) / TQ) * BH, K3_FWD_MINB, (Ns + TK - 1) / TK, tps);
+  return pick_split((long long)((Nq + TQ - 1) / TQ) * BH, FWD_MINB, (Ns + TK - 1) / TK, tps);
 }
 
 extern "C" size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward) {
@@ -486,8 +556,8 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, (float*)workspace, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_fwd pad")) return rc;
   dim3 grid((a.Nq + TQ - 1) / TQ, BH, a.split);
-  if (Dh == 32) rpe_attn_fwd_kernel<32><<<grid, TQ, 0, st>>>(a);
-  else rpe_attn_fwd_kernel<16><<<grid, TQ, 0, st>>>(a);
+  if (Dh == 32) rpe_attn_fwd_kernel<32><<<grid, TQ / RQ, 0, st>>>(a);
+  else rpe_attn_fwd_kernel<16><<<grid, TQ / RQ, 0, st>>>(a);
   if (int rc = check_launch("rpe_attn_fwd")) return rc;
   if (a.split > 1) {
     dim3 cgrid((a.Nq + 127) / 128, BH);
