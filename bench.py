@@ -366,8 +366,9 @@ def main():
     ncu_traffic = {"msda_bwd_kernel": 2.616e9, "msda_fwd_kernel": 1.240e9} if (dt == 0 and B == 8) else {}
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": ncu_traffic.get(dom[0]), "peak_source": peak_src,
-                "limiter": "bwd: SM->L2 request path (RED.ADD.F32x4 payload, 88% busy); fwd: L1 data-pipe wavefronts "
-                           "(one 128 B wavefront per tap, 73% busy) -- see DESIGN.md section 4",
+                "limiter": "bwd: L2 atomic units (655 M RED sectors/launch; RED.v4, TMA bulk reduce and tensor TMA reduce all "
+                           "measure 3.03 ms for the scatter alone); fwd: L1 data pipe (pure-gather ceiling 0.85 ms) -- "
+                           "profiles/r1_msda_ceilings.md, DESIGN.md section 4",
                 "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[2],
                 "fwd": {"ms": t_fwd, "GBps": ab_fwd / (t_fwd * 1e-3) / 1e9},
                 "bwd": {"ms": t_bwd, "GBps": ab_bwd / (t_bwd * 1e-3) / 1e9,
