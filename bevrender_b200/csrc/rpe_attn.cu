@@ -47,20 +47,25 @@ struct Bilin {
 // sample are loadable and out-of-table taps read the zero border -- exactly grid_sample's
 // padding_mode="zeros" -- so the inner loops carry no validity masks, no per-tap predicates and no
 // clamped indices (the bias lookup was 170 of the 237 instructions per (query, key) pair before).
-// Coordinates follow grid_sample(align_corners=True) on the displacement (query - key)/2, in the
-// reference's op order.
-__device__ __forceinline__ Bilin rpe_taps(float qy, float qx, float py, float px, int Rh, int Rw, int Wp) {
-  const float dy = (qy - py) * 0.5f, dx = (qx - px) * 0.5f;
-  float ix = ((dx + 1.f) * 0.5f) * (float)(Rw - 1);
-  float iy = ((dy + 1.f) * 0.5f) * (float)(Rh - 1);
+//
+// Coordinates: grid_sample(align_corners=True) on the displacement (query - key)/2 is, per axis,
+//   i = (((q - p) * 0.5 + 1) * 0.5) * (R - 1)  =  (q * c + c2) - p * c,   c = (R-1)/4, c2 = (R-1)/2  (both exact in fp32)
+// so the query half  A = fma(q, c, c2)  is formed once per query row and the key half  B = p * c  once per key when the
+// tile is staged; a pair costs one subtraction per axis instead of five operations.  Three roundings at magnitude <= R
+// against the reference's three: the coordinate differs from the reference's by ~1 ulp(R) (4e-6 cells at R = 111), far
+// inside the 1e-4 budget because the bilinear lookup is continuous.
+__device__ __forceinline__ float rpe_query_half(float q, int R) { return fmaf(q, 0.25f * (float)(R - 1), 0.5f * (float)(R - 1)); }
+__device__ __forceinline__ float rpe_key_half(float p, int R) { return p * (0.25f * (float)(R - 1)); }
+
+__device__ __forceinline__ Bilin rpe_taps(float ay, float ax, float by, float bx, int Rh, int Rw, int Wp) {
   // clamp to [-2, R]: a clamped sample has ALL four taps in the zero border, so its value and both of its
   // gradients vanish exactly as for an out-of-range grid_sample location (NaN maps to -2 as well)
-  ix = fminf(fmaxf(ix, -2.f), (float)Rw);
-  iy = fminf(fmaxf(iy, -2.f), (float)Rh);
+  const float ix = fminf(fmaxf(ax - bx, -2.f), (float)Rw);
+  const float iy = fminf(fmaxf(ay - by, -2.f), (float)Rh);
   Bilin b;
   const float x0f = floorf(ix), y0f = floorf(iy);
-  b.wx1 = ix - x0f; b.wx0 = (x0f + 1.f) - ix;
-  b.wy1 = iy - y0f; b.wy0 = (y0f + 1.f) - iy;
+  b.wx1 = ix - x0f; b.wx0 = 1.f - b.wx1;
+  b.wy1 = iy - y0f; b.wy0 = 1.f - b.wy1;
   b.off = (int)y0f * Wp + (int)x0f;
   return b;
 }
@@ -222,7 +227,7 @@ __global__ void __launch_bounds__(TQ / RQ, FWD_MINB) rpe_attn_fwd_kernel(const _
       lane_elem(o[r], c) = 0.f;
     }
     const int iy = iq[r] / a.Wq, ixq = iq[r] - iy * a.Wq;
-    qy[r] = grid_coord(iy, a.Hq); qx[r] = grid_coord(ixq, a.Wq);
+    qy[r] = rpe_query_half(grid_coord(iy, a.Hq), a.Rh); qx[r] = rpe_query_half(grid_coord(ixq, a.Wq), a.Rw);
     m[r] = -INFINITY; l[r] = 0.f;
   }
   const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
@@ -231,8 +236,10 @@ __global__ void __launch_bounds__(TQ / RQ, FWD_MINB) rpe_attn_fwd_kernel(const _
     __syncthreads();
     stage_transposed<TK, DH>(sK, kb, a.Ns, j0, 1.f);
     stage_transposed<TK, DH>(sV, vb, a.Ns, j0, 1.f);
-    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x)
-      sPos[jj] = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x) {
+      const float2 p = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+      sPos[jj] = make_float2(rpe_key_half(p.x, a.Rh), rpe_key_half(p.y, a.Rw));
+    }
     __syncthreads();
 #pragma unroll 1
     for (int jc = 0; jc < TK; jc += CH) {
@@ -360,15 +367,17 @@ __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const _
   const float lse = live ? __ldg(a.lse + (size_t)bh * a.Nq + i) : 0.f;
   const float delta = live ? __ldg(a.delta + (size_t)bh * a.Nq + i) : 0.f;
   const int iy = i / a.Wq, ixq = i - iy * a.Wq;
-  const float qy = grid_coord(iy, a.Hq), qx = grid_coord(ixq, a.Wq);
+  const float qy = rpe_query_half(grid_coord(iy, a.Hq), a.Rh), qx = rpe_query_half(grid_coord(ixq, a.Wq), a.Rw);
 
   const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
   for (int j0 = jbeg; j0 < jend; j0 += TK) {
     __syncthreads();
     stage_transposed<TK, DH>(sK, kb, a.Ns, j0, 1.f);
     stage_transposed<TK, DH>(sV, vb, a.Ns, j0, 1.f);
-    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x)
-      sPos[jj] = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x) {
+      const float2 p = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+      sPos[jj] = make_float2(rpe_key_half(p.x, a.Rh), rpe_key_half(p.y, a.Rw));
+    }
     __syncthreads();
     const int jn = min(TK, a.Ns - j0);
 #pragma unroll 4
@@ -427,6 +436,7 @@ __global__ void __launch_bounds__(TKB, K3_DKV_MINB) rpe_attn_bwd_dkv_kernel(cons
   }
   float2 pj = make_float2(0.f, 0.f);
   if (live) pj = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns + j);
+  pj = make_float2(rpe_key_half(pj.x, a.Rh), rpe_key_half(pj.y, a.Rw));
   float giy = 0.f, gix = 0.f;
   const bool want_bias_grad = (a.grad_rpe_pad != nullptr) || (a.grad_pos != nullptr);
 
@@ -440,7 +450,8 @@ __global__ void __launch_bounds__(TKB, K3_DKV_MINB) rpe_attn_bwd_dkv_kernel(cons
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < a.Nq) {
         const int iy = i / a.Wq, ixq = i - iy * a.Wq;
-        r = make_float4(grid_coord(iy, a.Hq), grid_coord(ixq, a.Wq), __ldg(a.lse + (size_t)bh * a.Nq + i),
+        r = make_float4(rpe_query_half(grid_coord(iy, a.Hq), a.Rh), rpe_query_half(grid_coord(ixq, a.Wq), a.Rw),
+                        __ldg(a.lse + (size_t)bh * a.Nq + i),
                         __ldg(a.delta + (size_t)bh * a.Nq + i));
       }
       sRow[ii] = r;
