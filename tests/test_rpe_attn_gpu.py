@@ -70,3 +70,22 @@ def test_rpe_attention_large_rows_vs_chunked_oracle():
     ones = torch.ones_like(v)
     oc = bb.rpe_attention(q.cuda(), k.cuda(), ones.cuda(), rpe.cuda(), pos.cuda(), N, N, 1)
     assert (oc - 1).abs().max() < 1e-5
+
+
+def test_rpe_attention_masked_reference_points():
+    """SCA with masked reference points (bev_cmr_proj.py:106-124): a third of the keys sit at (-1, -1) plus a
+    sub-cell offset, so whole warps of the key kernel hit the same four table cells (the pre-reduced atomic path)."""
+    import bevrender_b200 as bb
+    B, h, Hq, Wq, Hk, Wk = 1, 2, 14, 14, 7, 70
+    q, k, v, rpe, pos, go = _case(B, h, 1, Hq, Wq, Hk, Wk, 5, 5, 0.05)
+    Ns = Hk * Wk
+    pos[:, : Ns // 3] = -1.0 + 1e-3 * torch.randn(B, Ns // 3, 2)
+    cpu = [t.clone().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    ref = oda.rpe_attention_dense(*cpu, Hq, Wq, 1, 32 ** -0.5)
+    ref.backward(go)
+    dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    out = bb.rpe_attention(*dev, Hq, Wq, 1)
+    out.backward(go.cuda())
+    assert rel_err(out.cpu(), ref) < FP32_TOL
+    for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, cpu):
+        assert rel_err(a.grad.cpu(), b.grad) < FP32_TOL, name
