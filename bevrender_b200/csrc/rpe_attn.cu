@@ -151,7 +151,7 @@ __device__ __forceinline__ float& lane_elem(float2* r, int c) { return (c & 1) ?
 #define K3_CH 8
 #endif
 #ifndef K3_FWD_MINB
-#define K3_FWD_MINB 4
+#define K3_FWD_MINB 3
 #endif
 #ifndef K3_DQ_MINB
 #define K3_DQ_MINB 3
