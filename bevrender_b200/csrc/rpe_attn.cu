@@ -410,26 +410,43 @@ __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const _
 #endif
 constexpr int TKB = 128, TQB = K3_TQB;
 
+// K3_CS lanes share one key, each owning DH / K3_CS channels of k, v, dk, dv (the 128 registers of per-key state are what
+// limits this kernel to 8 warps per SM): the two half dot products are combined with one shuffle each, the bias, the
+// softmax probability and the bias gradients are evaluated by both lanes (identical values), and lane 0 of the pair
+// issues the atomics.
+#ifndef K3_CS
+#define K3_CS 1
+#endif
+#ifndef K3_DKV_MINB2
+#define K3_DKV_MINB2 2
+#endif
+constexpr int CS = K3_CS;
+constexpr int DKV_MINB = CS == 1 ? K3_DKV_MINB : K3_DKV_MINB2;
+
 template <int DH>
-__global__ void __launch_bounds__(TKB, K3_DKV_MINB) rpe_attn_bwd_dkv_kernel(const __grid_constant__ RpeArgs a) {
+__global__ void __launch_bounds__(TKB * CS, DKV_MINB) rpe_attn_bwd_dkv_kernel(const __grid_constant__ RpeArgs a) {
+  constexpr int DL = DH / CS;         // channels per lane
   __shared__ __align__(16) float sQ[TQB * PAD];
   __shared__ __align__(16) float sG[TQB * PAD];
-  __shared__ float4 sRow[TQB];    // qy, qx, lse, delta
-  const int bh = blockIdx.y, j = blockIdx.x * TKB + threadIdx.x;
+  __shared__ float4 sRow[TQB];    // query halves of the bias coordinates (y, x), lse, delta
+  const int bh = blockIdx.y, j = blockIdx.x * TKB + threadIdx.x / CS;
+  const int part = threadIdx.x % CS, c0 = part * DL;
   const bool live = j < a.Ns;
+  const unsigned lmask = __ballot_sync(0xffffffffu, live);    // lanes that run the pair loop (whole key groups)
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
   // the table gradient is a hot spot (every (query, key) pair of a head lands on ~12k cells): spread the atomics of
   // different CTAs over `gcopies` private copies, summed by rpe_unpad_add_kernel (-47 % backward time at N=56)
   float* gtable = a.grad_rpe_pad ? a.grad_rpe_pad + ((size_t)((blockIdx.x + blockIdx.y) % a.gcopies) * a.h + head) * a.Hp * a.Wp +
                                        2 * a.Wp + 2 : nullptr;
+  if (part != 0) gtable = nullptr;
   const float* qb = a.q + (size_t)bh * DH * a.Nq;
   const float* gb = a.grad_out + (size_t)bh * DH * a.Nq;
 
-  float2 kr[DH / 2], vr[DH / 2], dk[DH / 2], dv[DH / 2];
+  float2 kr[DL / 2], vr[DL / 2], dk[DL / 2], dv[DL / 2];
 #pragma unroll
-  for (int c = 0; c < DH; ++c) {
-    const size_t idx = ((size_t)bh * DH + c) * a.Ns + j;
+  for (int c = 0; c < DL; ++c) {
+    const size_t idx = ((size_t)bh * DH + c0 + c) * a.Ns + j;
     lane_elem(kr, c) = live ? __ldg(a.k + idx) : 0.f;
     lane_elem(vr, c) = live ? __ldg(a.v + idx) : 0.f;
     lane_elem(dk, c) = 0.f; lane_elem(dv, c) = 0.f;
@@ -464,12 +481,18 @@ __global__ void __launch_bounds__(TKB, K3_DKV_MINB) rpe_attn_bwd_dkv_kernel(cons
       const float4 r = sRow[ii];
       const Bilin b = rpe_taps(r.x, r.y, pj.x, pj.y, a.Rh, a.Rw, a.Wp);
       float tv[4];
-      const float s = dot32<DH>(kr, sQ + ii * PAD) + rpe_bias(table, b, a.Wp, tv);
+      float qk = dot32<DL>(kr, sQ + ii * PAD + c0);
+      float dp = dot32<DL>(vr, sG + ii * PAD + c0);
+#pragma unroll
+      for (int sh = 1; sh < CS; sh <<= 1) {
+        qk += __shfl_xor_sync(lmask, qk, sh);
+        dp += __shfl_xor_sync(lmask, dp, sh);
+      }
+      const float s = qk + rpe_bias(table, b, a.Wp, tv);
       const float pr = __expf(s - r.z);
-      axpy32<DH>(dv, pr, sG + ii * PAD);
-      const float dp = dot32<DH>(vr, sG + ii * PAD);
+      axpy32<DL>(dv, pr, sG + ii * PAD + c0);
       const float ds = pr * (dp - r.w);
-      axpy32<DH>(dk, ds, sQ + ii * PAD);
+      axpy32<DL>(dk, ds, sQ + ii * PAD + c0);
       if (want_bias_grad) {
         gix = fmaf(ds, b.wy0 * (tv[1] - tv[0]) + b.wy1 * (tv[3] - tv[2]), gix);
         giy = fmaf(ds, b.wx0 * (tv[2] - tv[0]) + b.wx1 * (tv[3] - tv[1]), giy);
@@ -485,8 +508,8 @@ __global__ void __launch_bounds__(TKB, K3_DKV_MINB) rpe_attn_bwd_dkv_kernel(cons
   }
   if (live) {
 #pragma unroll
-    for (int c = 0; c < DH; ++c) {
-      const size_t idx = ((size_t)bh * DH + c) * a.Ns + j;
+    for (int c = 0; c < DL; ++c) {
+      const size_t idx = ((size_t)bh * DH + c0 + c) * a.Ns + j;
       if (a.split == 1) {
         if (a.grad_k) a.grad_k[idx] = lane_elem(dk, c);    // sQ already carries `scale`
         if (a.grad_v) a.grad_v[idx] = lane_elem(dv, c);
@@ -495,7 +518,7 @@ __global__ void __launch_bounds__(TKB, K3_DKV_MINB) rpe_attn_bwd_dkv_kernel(cons
         if (a.grad_v) atomicAdd(a.grad_v + idx, lane_elem(dv, c));
       }
     }
-    if (a.grad_pos) {
+    if (a.grad_pos && part == 0) {
       // table coord = (Rx-1) * ((q - pos)/4 + 1/2)  ->  d coord / d pos = -(Rx-1)/4
       float* gp = a.grad_pos + ((size_t)bg * a.Ns + j) * 2;
       atomicAdd(gp, giy * (-0.25f * (float)(a.Rh - 1)));
@@ -615,13 +638,13 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   }
   if (grad_k || grad_v || grad_rpe || grad_pos) {
     const int nkt = (Ns + TKB - 1) / TKB;
-    a.split = pick_split((long long)nkt * BH, 2, (a.Nq + TQB - 1) / TQB, &a.tiles_per_split);
+    a.split = pick_split((long long)nkt * BH, DKV_MINB < 2 ? 2 : DKV_MINB, (a.Nq + TQB - 1) / TQB, &a.tiles_per_split);
     if (a.split > 1) {
       if (grad_k) cudaMemsetAsync(grad_k, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
       if (grad_v) cudaMemsetAsync(grad_v, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
     }
-    if (Dh == 32) rpe_attn_bwd_dkv_kernel<32><<<dim3(nkt, BH, a.split), TKB, 0, st>>>(a);
-    else rpe_attn_bwd_dkv_kernel<16><<<dim3(nkt, BH, a.split), TKB, 0, st>>>(a);
+    if (Dh == 32) rpe_attn_bwd_dkv_kernel<32><<<dim3(nkt, BH, a.split), TKB * CS, 0, st>>>(a);
+    else rpe_attn_bwd_dkv_kernel<16><<<dim3(nkt, BH, a.split), TKB * CS, 0, st>>>(a);
     if (int rc = check_launch("rpe_attn_bwd dkv")) return rc;
   }
   if (grad_rpe) {
