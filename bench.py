@@ -383,7 +383,8 @@ def main():
     h2d = sum(t.numel() * t.element_size() for t in h_in.values())
     d2h = sum(t.numel() * t.element_size() for t in h_out.values())
     pipe = None if args.no_e2e else HostMsdaPipeline(shapes, starts, HEADS, DH, Nq, POINTS, N_SIDE, tdt, dev,
-                                                    qsplit=int(os.environ.get("BEVR_QSPLIT", "4")))
+                                                    qsplit=int(os.environ.get("BEVR_QSPLIT", "4")),
+                                                    nslots=int(os.environ.get("BEVR_NSLOTS", "2")))
 
     def e2e_step():
         pipe.run(h_in, h_out)

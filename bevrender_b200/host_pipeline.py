@@ -1,9 +1,10 @@
 """Host-buffer entry point of the MSDA gather: pinned HOST inputs -> device -> fwd+bwd -> pinned HOST results.
 
 This is the call a user holding host-resident tensors makes (``bench.py``'s ``e2e`` leg).  The batch flows through
-three CUDA streams (H2D, compute through the C ABI, D2H) over a double-buffered device staging area, so the PCIe
+three CUDA streams (H2D, compute through the C ABI, D2H) over ``nslots`` device staging slots, so the PCIe
 uploads of the next piece and the downloads of the previous one overlap the kernels of the current one (PCIe is
-full duplex; the kernels are ~1/10 of the transfer time).
+full duplex; the kernels are ~1/10 of the transfer time).  Two slots suffice: three or four measure the same
+30.8 ms/step (the link itself gives 26.1 ms for 1.25 GB each way at once, 22.6 ms one way, scripts/exp_pcie.py).
 
 Pieces: a sample's ``value`` goes up first, then its queries in ``qsplit`` row blocks (coordinates, weights,
 ``grad_out`` up; ``out``, ``grad_loc``, ``grad_weight`` down); every block's backward accumulates into the sample's
@@ -25,7 +26,7 @@ _ACCUMULATE = 8
 
 class HostMsdaPipeline:
     def __init__(self, spatial_shapes, level_start_index, h, Dh, Nq, P, query_w, dtype=torch.float32,
-                 device=None, chunk=1, flags=0, qsplit=4):
+                 device=None, chunk=1, flags=0, qsplit=4, nslots=2):
         self.dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.shapes, self.L = list(spatial_shapes), len(spatial_shapes)
         self.S = sum(hh * ww for hh, ww in spatial_shapes)
@@ -47,9 +48,10 @@ class HostMsdaPipeline:
         shp_out = {"out": ((c, Nq, h * Dh), dtype), "grad_value": ((c, self.S, h, Dh), dtype),
                    "grad_loc": ((c, Nq, h, self.L, P, 2), f32), "grad_weight": ((c, Nq, h, self.L, P), dtype)}
         mk = lambda d: {k: torch.empty(s, dtype=t, device=self.dev) for k, (s, t) in d.items()}
-        self.slots = [{"in": mk(shp_in), "out": mk(shp_out)} for _ in range(2)]
+        self.nslots = nslots
+        self.slots = [{"in": mk(shp_in), "out": mk(shp_out)} for _ in range(nslots)]
         nws = _lib.lib().bevr_msda_bwd_workspace_bytes(c, self.S, h, Dh, self.dt)
-        self.ws = [torch.empty(max(nws, 16), dtype=torch.uint8, device=self.dev) for _ in range(2)]
+        self.ws = [torch.empty(max(nws, 16), dtype=torch.uint8, device=self.dev) for _ in range(nslots)]
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
 
     def bytes_per_sample(self):
@@ -64,17 +66,18 @@ class HostMsdaPipeline:
         cur = torch.cuda.current_stream(self.dev)
         for s in (self.s_in, self.s_cmp, self.s_out):
             s.wait_stream(cur)
-        ev_out = [None, None]
+        ns = self.nslots
+        ev_out = [None] * ns
         c = self.chunk
         split = len(self.qblocks) > 1 and c == 1
         blocks = self.qblocks if split else [(0, self.Nq)]
         cs = C.c_void_p(self.s_cmp.cuda_stream)
         for i in range(B // c):
-            slot, sl = self.slots[i % 2], slice(i * c, (i + 1) * c)
+            slot, sl = self.slots[i % ns], slice(i * c, (i + 1) * c)
             a, o = slot["in"], slot["out"]
             with torch.cuda.stream(self.s_in):
-                if ev_out[i % 2] is not None:
-                    self.s_in.wait_event(ev_out[i % 2])            # slot drained by chunk i-2
+                if ev_out[i % ns] is not None:
+                    self.s_in.wait_event(ev_out[i % ns])           # slot drained by chunk i - nslots
                 a["value"].copy_(h_in["value"][sl], non_blocking=True)
             for bi, (q0, q1) in enumerate(blocks):
                 with torch.cuda.stream(self.s_in):
@@ -90,7 +93,7 @@ class HostMsdaPipeline:
                                                self.flags, cs), "bevr_msda_fwd")
                     _lib.check(L.bevr_msda_bwd(P(a["value"]), self.hw, self.st, P(loc), None, P(w), P(go),
                                                P(o["grad_value"]), P(o["grad_loc"][:, q0:q1]),
-                                               P(o["grad_weight"][:, q0:q1]), P(self.ws[i % 2]), c, self.S, self.h,
+                                               P(o["grad_weight"][:, q0:q1]), P(self.ws[i % ns]), c, self.S, self.h,
                                                self.Dh, nq, self.L, self.P, self.query_w, self.dt,
                                                self.flags | (_ACCUMULATE if bi > 0 else 0), cs), "bevr_msda_bwd")
                     ev_cmp = self.s_cmp.record_event()
@@ -100,6 +103,6 @@ class HostMsdaPipeline:
                         h_out[k][sl, q0:q1].copy_(o[k][:, q0:q1], non_blocking=True)
                     if bi == len(blocks) - 1:
                         h_out["grad_value"][sl].copy_(o["grad_value"], non_blocking=True)
-                        ev_out[i % 2] = self.s_out.record_event()
+                        ev_out[i % ns] = self.s_out.record_event()
         for s in (self.s_in, self.s_cmp, self.s_out):
             cur.wait_stream(s)
