@@ -108,6 +108,25 @@ class ClockSampler:
                 "reasons": sorted(self.reasons), "samples": len(sm), "source": "nvml" if self.nvml else "nvidia-smi"}
 
 
+_JSON_OUT = None
+
+
+def claim_stdout():
+    """stdout carries exactly ONE JSON line: keep a private handle on the real stdout and point file descriptor 1 at
+    stderr, so anything a library prints there (NCCL's "NCCL version ..." banner under torchrun) cannot get in."""
+    global _JSON_OUT
+    if _JSON_OUT is None:
+        sys.stdout.flush()
+        _JSON_OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _JSON_OUT if _JSON_OUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def bind_to_gpu_numa_node(local_rank):
     """Pin this process to the CPUs NVML reports as closest to its GPU BEFORE any pinned host buffer is
     allocated, so the staging pages of the e2e leg are first-touched on the GPU's own NUMA node (with 8 ranks
@@ -159,7 +178,7 @@ def run_reference(args):
                              "sample": "1 of 8 samples per step (40000 queries), fwd+bwd, torch CPU grid_sample path"},
             "e2e": {"value": v, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(B, dtype):
@@ -230,7 +249,7 @@ def run_train(args):
     ms /= args.steps
     if rank == 0:
         nparam = sum(p.numel() for p in live)
-        print(json.dumps({"metric": "train samples/s", "value": world * B / (ms * 1e-3), "unit": "samples/s",
+        emit({"metric": "train samples/s", "value": world * B / (ms * 1e-3), "unit": "samples/s",
                           "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
                           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
                           "data": "synthetic", "loss": float(loss.detach()),
@@ -238,12 +257,13 @@ def run_train(args):
                                      "image 128x160, C=64, 2 heads, D=5" % n, "batch_per_gpu": B,
                                      "parallelism": "dp%d, flat fp32 gradient bucket (%d params, %.1f MB), 2 NCCL "
                                      "allreduce(AVG) launches overlapped with backward" % (world, nparam, nparam * 4 / 1e6)},
-                          "clocks": clk.summary()}), flush=True)
+                          "clocks": clk.summary()})
     if world > 1:
         dist.destroy_process_group()
 
 
 def main():
+    claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -418,7 +438,7 @@ def main():
                 "vs_baseline": None, "dtype": "f32" if dt == 0 else "bf16", "data": "synthetic",
                 "config": workload_config(B, args.dtype), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": args.steps * n_k, "clocks": clk.summary()}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
