@@ -75,3 +75,29 @@ def test_product_never_imports_the_oracle():
             if f.endswith(".py"):
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_offset_head_validation_and_empty_batch():
+    from bevrender_b200 import _lib
+    L = _lib.lib()
+    # 9 output channels exceed the kernel's 8; the plain layout needs exactly 2; the interleaved one an even H
+    assert L.bevr_offset_head_fwd(None, None, None, None, None, 0, None, None, 1, 8, 4, 4, 9, 1, 1, 0.5, 1e-5, None) < 0
+    assert b"output channels" in L.bevr_last_error()
+    assert L.bevr_offset_head_fwd(None, None, None, None, None, 0, None, None, 1, 8, 4, 4, 3, 0, 1, 0.5, 1e-5, None) < 0
+    assert L.bevr_offset_head_fwd(None, None, None, None, None, 0, None, None, 1, 8, 5, 4, 4, 1, 1, 0.5, 1e-5, None) < 0
+    assert L.bevr_offset_head_fwd(None, None, None, None, None, 0, None, None, 1, 8, 4, 4, 2, 0, 1, 0.5, 1e-5, None) < 0  # NULLs
+    assert L.bevr_offset_head_fwd(None, None, None, None, None, 0, None, None, 0, 8, 4, 4, 2, 0, 1, 0.5, 1e-5, None) == 0
+    assert L.bevr_offset_head_bwd(None, None, None, None, None, 0, None, None, None, None, None, None, 0, 8, 4, 4, 2, 0, 1,
+                                  0.5, 1e-5, None) == 0
+
+
+def test_rpe_attention_workspace_covers_the_forward_split():
+    """The forward's key-range partials live in the caller's workspace: the size query must grow with B*h*Nq when the
+    grid is small enough to be split, and not for large grids."""
+    from bevrender_b200 import _lib
+    L = _lib.lib()
+    table = 2 * (111 + 4) * (111 + 4) * 4
+    small = L.bevr_rpe_attn_workspace_bytes(16, 2, 32, 3136, 3136, 111, 111, 0)
+    assert small > table + 16 * 34 * 3136 * 4            # at least two ranges of (Dh + 2) floats per row
+    big = L.bevr_rpe_attn_workspace_bytes(8, 8, 32, 40000, 40000, 399, 399, 0)
+    assert big == 8 * 403 * 403 * 4                       # 2504 CTAs already: no split, padded table only
