@@ -3,9 +3,10 @@
 ``TSADeformableAttention`` / ``SCADeformableAttention`` keep the constructor arguments, parameter
 names and shapes (so ``state_dict``s interchange) and the forward signatures of
 model/TSA_deform_attn.py:14-337 and model/SCA_deform_attn.py:14-421, and therefore drop into
-model/TSA.py / model/SCA.py / model/encoder.py unchanged.  The offset network and the 1x1
-projections stay PyTorch; the feature gather (K1/K2) and the attention with
-sampled relative-position bias (K3) run as sm_100a kernels behind the C ABI.
+model/TSA.py / model/SCA.py / model/encoder.py unchanged.  The depthwise convolution of the offset
+network and the 1x1 K/V/out projections stay PyTorch; the rest of the offset
+network up to the sampling positions (fused offset head, row f-2), the feature gather (K1/K2) and the
+attention with sampled relative-position bias (K3) run as sm_100a kernels behind the C ABI.
 
 Differences from the reference, all deliberate:
   * nothing of size (Nq, Ns) is materialised (the reference needs 51 GB/sample at 200x200);
@@ -100,18 +101,6 @@ class _DeformAttnBase(nn.Module):
         return offset_head(net[0](xq), ln.weight, ln.bias, net[3].weight, ref, interleave=interleave,
                            scaled=bool(self.scale_offset_range),
                            factor=self.offset_range_factor if self.scale_offset_range else 1.0, eps=ln.eps)
-
-    def _scaled_positions(self, raw, ref):
-        """raw (B*g, 2, Hk, Wk) offset-net output in (y, x); ref (B*g, Hk, Wk, 2)."""
-        Hk, Wk = raw.shape[-2:]
-        if self.scale_offset_range:
-            key = ("rng", Hk, Wk, str(raw.device))
-            if key not in self._grids:           # built once per shape: no per-forward host->device copy
-                self._grids[key] = torch.tensor([1.0 / (Hk - 1.0), 1.0 / (Wk - 1.0)],
-                                                device=raw.device).reshape(1, 2, 1, 1)
-            raw = raw.tanh().mul(self._grids[key]).mul(self.offset_range_factor)
-        pos = raw.permute(0, 2, 3, 1) + ref
-        return pos if self.scale_offset_range else pos.clamp(-1.0, +1.0)
 
     @staticmethod
     def _pointwise(conv, x):
