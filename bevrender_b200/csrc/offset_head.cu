@@ -9,8 +9,9 @@
 //
 // Mapping: 4 lanes own one pixel (each a quarter of the channels, interleaved), 8 consecutive pixels per warp, so a
 // warp-wide load touches four 32-byte sectors; per-pixel reductions are two shuffles.  Parameter gradients are
-// reduced over the 8 pixels of a warp with shuffles, then over the CTA in shared memory, then one global atomic
-// per (CTA, parameter).
+// reduced over the 8 pixels of a warp with shuffles into a shared-memory accumulator PRIVATE to the warp (channel c
+// is only ever touched by lane 0 of slice c % 4, so plain read-modify-writes suffice -- shared fp32 atomics are CAS
+// loops), then over the CTA's warps, then one global atomic per (CTA, parameter).
 #include "bevr_common.cuh"
 
 namespace bevr {
@@ -77,14 +78,14 @@ __global__ void __launch_bounds__(OH_THREADS) offset_head_kernel(const __grid_co
   float* s_gamma = sm;
   float* s_beta = sm + Cm;
   float* s_w1 = sm + 2 * Cm;                 // [O][Cm]
-  float* s_acc = sm + (2 + O) * Cm;          // backward: grad_gamma[Cm], grad_beta[Cm], grad_w1[O][Cm]
+  float* s_acc = sm + (2 + O) * Cm;          // backward, one copy per warp: grad_gamma[Cm], grad_beta[Cm], grad_w1[O][Cm]
   for (int i = threadIdx.x; i < Cm; i += blockDim.x) { s_gamma[i] = a.gamma[i]; s_beta[i] = a.beta[i]; }
   for (int i = threadIdx.x; i < O * Cm; i += blockDim.x) s_w1[i] = a.w1[i];
-  if (BWD)
-    for (int i = threadIdx.x; i < (2 + O) * Cm; i += blockDim.x) s_acc[i] = 0.f;
-  __syncthreads();
-
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+  if (BWD)
+    for (int i = threadIdx.x; i < nwarp * (2 + O) * Cm; i += blockDim.x) s_acc[i] = 0.f;
+  __syncthreads();
+  float* w_acc = s_acc + warp * (2 + O) * Cm;
   const int pl = lane & 7, s = lane >> 3;
   const unsigned smask = 0xffu << (8 * s);
   const long long HW = (long long)a.H * a.W;
@@ -175,14 +176,14 @@ __global__ void __launch_bounds__(OH_THREADS) offset_head_kernel(const __grid_co
       s2 = fmaf(dyh, yh, s2);
       // parameter gradients: sum over the warp's 8 pixels, one shared-memory atomic per (warp, parameter)
       const float gg = pixel_sum(smask, dz * yh), gb = pixel_sum(smask, dz);
-      if (pl == 0) { atomicAdd(s_acc + c, gg); atomicAdd(s_acc + Cm + c, gb); }
+      if (pl == 0) { w_acc[c] += gg; w_acc[Cm + c] += gb; }
       if (a.grad_w1) {
         const float g = gelu_f(z);
 #pragma unroll
         for (int o = 0; o < OH_OMAX; ++o)
           if (o < O) {
             const float gw = pixel_sum(smask, draw[o] * g);
-            if (pl == 0) atomicAdd(s_acc + (2 + o) * Cm + c, gw);
+            if (pl == 0) w_acc[(2 + o) * Cm + c] += gw;
           }
       }
     }
@@ -206,12 +207,13 @@ __global__ void __launch_bounds__(OH_THREADS) offset_head_kernel(const __grid_co
   }
   if (BWD) {
     __syncthreads();
-    for (int i = threadIdx.x; i < Cm; i += blockDim.x) {
-      if (a.grad_gamma) atomicAdd(a.grad_gamma + i, s_acc[i]);
-      if (a.grad_beta) atomicAdd(a.grad_beta + i, s_acc[Cm + i]);
+    const int np = (2 + O) * Cm;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) {
+      float v = 0.f;
+      for (int w = 0; w < nwarp; ++w) v += s_acc[w * np + i];
+      float* dst = i < Cm ? a.grad_gamma : (i < 2 * Cm ? a.grad_beta : a.grad_w1);
+      if (dst) atomicAdd(dst + (i < Cm ? i : (i < 2 * Cm ? i - Cm : i - 2 * Cm)), v);
     }
-    if (a.grad_w1)
-      for (int i = threadIdx.x; i < O * Cm; i += blockDim.x) atomicAdd(a.grad_w1 + i, s_acc[2 * Cm + i]);
   }
 }
 
@@ -234,7 +236,7 @@ static int fill(OffArgs& a, int Bg, int Cm, int H, int W, int O, int interleave,
 
 template <bool BWD>
 static int launch_oh(const OffArgs& a, cudaStream_t st, const char* what) {
-  const size_t smem = (size_t)(BWD ? 2 : 1) * (2 + a.O) * a.Cm * sizeof(float);
+  const size_t smem = (size_t)(BWD ? 1 + OH_THREADS / 32 : 1) * (2 + a.O) * a.Cm * sizeof(float);
   BEVR_REQUIRE(smem <= 200 * 1024, "offset_head: Cm=%d needs %zu B of shared memory", a.Cm, smem);
   if (smem > 48 * 1024)
     cudaFuncSetAttribute(offset_head_kernel<BWD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
