@@ -2,7 +2,7 @@
 
 Restates ``SpatialCrossAttn.sample_3d_points`` (SCA.py:112-162) and
 ``BEV2CameraProjector.bev_grid_to_camera`` / ``get_in_bound_mask``
-(bev_cmr_proj.py:61-124, ``remove_ref_in_gray=False``) with the same torch CPU
+(bev_cmr_proj.py:61-124, incl. the ``remove_ref_in_gray`` image test) with the same torch CPU
 primitives the reference calls (``inverse``, ``@``, ``div``, ``to(int32)``), and
 additionally returns the truncated pixel indices and the validity mask that the
 reference folds into the coordinates -- those are the integer outputs the CUDA
@@ -39,8 +39,10 @@ def scale_intrinsics(K, img_w, img_h, ori_w, ori_h):
     return torch.tensor(K).float()
 
 
-def project_points(points_3d, imu_to_cam, K_scaled, img_w, img_h):
-    """points_3d (4,h,w,z) fp32 -> uv (2,h,w,z) in [-1,1], pix (2,h,w,z) int32, mask (h,w,z) bool."""
+def project_points(points_3d, imu_to_cam, K_scaled, img_w, img_h, gray_image=None):
+    """points_3d (4,h,w,z) fp32 -> uv (2,h,w,z) in [-1,1], pix (2,h,w,z) int32, mask (h,w,z) bool.
+    ``gray_image`` (H, W, 3) uint8: remove_ref_in_gray=True, i.e. points whose truncated pixel is (128,128,128)
+    in that image are masked too (bev_cmr_proj.py:114-122)."""
     shp = points_3d.shape[1:]
     p = points_3d.reshape(4, -1)
     T = torch.as_tensor(imu_to_cam).float()
@@ -49,6 +51,10 @@ def project_points(points_3d, imu_to_cam, K_scaled, img_w, img_h):
     uv = uvw.div(uvw[-1])[:2]
     pix = uv.to(torch.int32)
     mask = pix[1].ge(0) & pix[1].lt(img_h - 1) & pix[0].ge(0) & pix[0].lt(img_w - 1)
+    if gray_image is not None:
+        img = torch.as_tensor(np.asarray(gray_image)).permute(2, 0, 1)          # pil_to_tensor layout (3, H, W)
+        q = pix.masked_fill(~mask, 0).long()
+        mask = mask & ((img[:, q[1], q[0]] == 128).sum(0) != 3)
     uv = uv.masked_fill(~mask, 0)
     uv[0] = uv[0] / (img_w - 1)
     uv[1] = uv[1] / (img_h - 1)

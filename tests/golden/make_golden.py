@@ -142,6 +142,36 @@ def make_proj(name, N, D, bound, z_shift, yaw_deg, pitch_deg, img_w=160, img_h=1
     return uv
 
 
+def make_proj_gray(name, N=28, D=4, img_w=160, img_h=128, seed=29):
+    """remove_ref_in_gray=True (bev_cmr_proj.py:114-122): points that land on a (128,128,128) pixel of a
+    reference image are masked as well.  The image (random colours, a gray band) is stored in the golden."""
+    import tempfile
+    from PIL import Image
+    _, _, Projector, SpatialCrossAttn = load_reference()
+    rng = np.random.default_rng(seed)
+    img = rng.integers(0, 256, size=(img_h, img_w, 3), dtype=np.uint8)
+    img[img_h // 2:, img_w // 3: 2 * img_w // 3] = 128                  # gray band where the ground projects
+    img[5:9, 7:30, 0] = 128                                             # one channel only: must NOT be masked
+    T, K = camera_setup(0.0)
+    bound = {"X": 20.0, "Y": 10.0, "Z": 2.0}
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "ref.png")
+        Image.fromarray(img).save(path)
+        proj = Projector(imu_to_rgb={0: [T.copy()]}, K={0: [K.copy()]}, vehicle_type_code=0, img_width=img_w,
+                         img_height=img_h, ori_img_width=640, ori_img_height=512, remove_ref_in_gray=True,
+                         bound_check_img_paths=[path], device="cpu")
+        stub = types.SimpleNamespace(bev_bound=bound, bev_feat_shape=N, bev_depth_dim=D, z_shift=-1.0)
+        pts = SpatialCrossAttn.sample_3d_points(stub)
+        uv = proj.bev_grid_to_camera(pts)[0][0]
+        p = pts.reshape(4, -1)
+        cam = proj.imu_to_cmr[0][0].inverse() @ p
+        uvw = proj.K[0][0][:, :3] @ cam[:3]
+        mask = proj.get_in_bound_mask(uvw.div(uvw[-1])[:2], 0, 0)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), cfg=np.array([N, D, img_w, img_h, 640, 512]), imu_to_cam=T,
+                        K=K, image=img, points=pts.numpy(), uv=uv.numpy(), mask=mask.reshape(pts.shape[1:]).numpy())
+    print(name, "valid", float(mask.float().mean()))
+
+
 def make_sca(name, N, D, C, h, g, B, Hi, Wi, scale_offset_range=True, seed=0):
     _, SCA, Projector, SpatialCrossAttn = load_reference()
     torch.manual_seed(seed)
@@ -232,6 +262,7 @@ def main():
     make_proj("proj_n200", 200, 4, bound, -1.0, 0.0, 0.0)
     make_proj("proj_yaw", 56, 5, bound, -1.0, 75.0, 10.0)          # most points off-image / behind
     make_proj("proj_z0", 28, 4, {"X": 20.0, "Y": 10.0, "Z": 2.0}, 1.0, 90.0, 0.0)  # z_cam == 0 rows
+    make_proj_gray("proj_gray")
 
 
 if __name__ == "__main__":

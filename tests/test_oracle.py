@@ -106,3 +106,16 @@ def test_msda_oracle_matches_numpy_restatement():
         acc += (bilinear.grid_sample_bilinear(vl, gl, False) * wl).sum(-1)
     ref = torch.from_numpy(acc).reshape(B, h * Dh, -1).transpose(1, 2)
     assert rel_err(out, ref) < 1e-12
+
+
+def test_projection_oracle_gray_mask_bit_exact():
+    """remove_ref_in_gray=True: golden made by the reference class with a reference image on disk."""
+    g, _, _ = load_golden("proj_gray")
+    N, D, W, H, oW, oH = [int(v) for v in g["cfg"]]
+    Ks = projection.scale_intrinsics(g["K"], W, H, oW, oH)
+    pts = torch.from_numpy(g["points"])
+    uv, _, mask = projection.project_points(pts, g["imu_to_cam"], Ks, W, H, gray_image=g["image"])
+    plain = projection.project_points(pts, g["imu_to_cam"], Ks, W, H)[2]
+    assert np.array_equal(mask.numpy(), g["mask"])
+    assert np.array_equal(uv.numpy().view(np.uint32), g["uv"].view(np.uint32))
+    assert int(plain.sum()) > int(mask.sum()) > 0          # the gray band really removes points
