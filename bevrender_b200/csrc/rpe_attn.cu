@@ -304,6 +304,220 @@ __global__ void __launch_bounds__(TQ / RQ, FWD_MINB) rpe_attn_fwd_kernel(const _
   }
 }
 
+// ------------------------------------------------------------------ forward, contractions on mma.sync (3xTF32)
+// The two contractions of the forward (S = Q^T K and O += P V) as legacy warp-level mma.sync.m16n8k8 TF32 with the
+// big/small operand split (x = hi + lo, hi = tf32(x); hi*hi + hi*lo + lo*hi accumulate in fp32): the dropped lo*lo term
+// and the truncation of lo are ~2^-22 relative, i.e. fp32-grade, which a single TF32 product (2^-11) is not.  SURVEY.md
+// appendix E allows CUDA-core FMA or legacy mma.sync here; tcgen05 stays reserved for the correlation.  The bias lookup,
+// the online softmax and the rescaling stay on the CUDA cores and now dominate the instruction count (~1.6 warp
+// instructions per (query, key) pair against 3.0 for the FFMA2 kernel, whose fma pipe alone needs 0.73 SM cycles per pair).
+//
+// One warp owns 16 query rows (accumulator layout of the m16n8 tile: lane = 4*g + t holds rows g and g+8, columns 2t,
+// 2t+1).  K, V tiles are staged pre-split (hi / lo) with a 36-float row pitch, which makes both B-operand access
+// patterns bank-conflict free.  For O += P V the eight keys of a k-step are fed in the order (0,2,4,6,1,3,5,7): operand
+// column t is key 2t and column t+4 is key 2t+1, so the probabilities are consumed in the registers they were computed in.
+#ifndef K3_FWD_MMA
+#define K3_FWD_MMA 1
+#endif
+constexpr int TQM = 64;                      // query rows per CTA (4 warps x 16)
+#ifndef K3_MMA_CH
+#define K3_MMA_CH 32
+#endif
+#ifndef K3_MMA_MINB
+#define K3_MMA_MINB 4
+#endif
+constexpr int CHM = K3_MMA_CH;               // keys per online-softmax step (4 n-tiles)
+
+__device__ __forceinline__ uint32_t tf32_hi(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return u;
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// rows [j0, j0+T) of a channel-major (DH, n) matrix as hi[T][PAD] / lo[T][PAD] (zero beyond n)
+template <int T, int DH>
+__device__ __forceinline__ void stage_split(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ src,
+                                            int n, int j0) {
+  for (int idx = threadIdx.x; idx < T * DH; idx += blockDim.x) {
+    const int c = idx / T, jj = idx - c * T;
+    const int j = j0 + jj;
+    const float x = j < n ? __ldg(src + (size_t)c * n + j) : 0.f;
+    const float h = __uint_as_float(tf32_hi(x));
+    hi[jj * PAD + c] = h;
+    lo[jj * PAD + c] = x - h;
+  }
+}
+
+template <int DH>
+__global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(const __grid_constant__ RpeArgs a) {
+  constexpr int KS = DH / 8;                 // k-steps of S = Q^T K (channels) = n-tiles of O (channels)
+  constexpr int NT = CHM / 8;                // key n-tiles per softmax step = k-steps of O += P V
+  __shared__ __align__(16) float sKh[TK * PAD], sKl[TK * PAD], sVh[TK * PAD], sVl[TK * PAD];
+  __shared__ __align__(16) float2 sPos[TK];
+  const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int head = bh % a.h, bg = bh / a.hpg;
+  const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
+  const float* kb = a.k + (size_t)bh * DH * a.Ns;
+  const float* vb = a.v + (size_t)bh * DH * a.Ns;
+  const float2* pb = reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns;
+
+  const int i0 = blockIdx.x * TQM + warp * 16;
+  int iq[2] = {i0 + g, i0 + g + 8};
+  float ay[2], ax[2], m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+  uint32_t qh[KS][4], ql[KS][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int iy = iq[r] / a.Wq, ixq = iq[r] - iy * a.Wq;
+    ay[r] = rpe_query_half(grid_coord(iy, a.Hq), a.Rh);
+    ax[r] = rpe_query_half(grid_coord(ixq, a.Wq), a.Rw);
+  }
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {            // a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
+      const int r = e & 1, c = ks * 8 + t + ((e >> 1) << 2);
+      const float x = iq[r] < a.Nq ? __ldg(a.q + ((size_t)bh * DH + c) * a.Nq + iq[r]) * a.scale : 0.f;
+      qh[ks][e] = tf32_hi(x);
+      ql[ks][e] = __float_as_uint(x - __uint_as_float(qh[ks][e]));
+    }
+  float o[KS][4];
+#pragma unroll
+  for (int nv = 0; nv < KS; ++nv)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[nv][e] = 0.f;
+
+  const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
+  for (int j0 = jbeg; j0 < jend; j0 += TK) {
+    __syncthreads();
+    stage_split<TK, DH>(sKh, sKl, kb, a.Ns, j0);
+    stage_split<TK, DH>(sVh, sVl, vb, a.Ns, j0);
+    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x) {
+      const float2 p = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+      sPos[jj] = make_float2(rpe_key_half(p.x, a.Rh), rpe_key_half(p.y, a.Rw));
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int jc = 0; jc < TK; jc += CHM) {
+      if (j0 + jc >= a.Ns) break;
+      // ---- scores of 16 rows x 32 keys
+      float sc[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) { sc[nt][0] = 0.f; sc[nt][1] = 0.f; sc[nt][2] = 0.f; sc[nt][3] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t kh[NT][2], kl[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int off = (jc + nt * 8 + g) * PAD + ks * 8 + t;      // B[k = t (+4)][n = g] = K[key g][channel t (+4)]
+          kh[nt][0] = __float_as_uint(sKh[off]); kh[nt][1] = __float_as_uint(sKh[off + 4]);
+          kl[nt][0] = __float_as_uint(sKl[off]); kl[nt][1] = __float_as_uint(sKl[off + 4]);
+        }
+        // the three products of one accumulator are issued NT tiles apart (they depend on each other)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], qh[ks], kh[nt][0], kh[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], qh[ks], kl[nt][0], kl[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ql[ks], kh[nt][0], kh[nt][1]);
+      }
+      // ---- + sampled bias; element e of tile nt: row (e >> 1), key jc + nt*8 + 2t + (e & 1)
+      float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float4 pp = *reinterpret_cast<const float4*>(&sPos[jc + nt * 8 + 2 * t]);   // two keys' halves
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1, kk = e & 1;
+          const Bilin b = rpe_taps(ay[r], ax[r], kk ? pp.z : pp.x, kk ? pp.w : pp.y, a.Rh, a.Rw, a.Wp);
+          float tv[4];
+          const float v = sc[nt][e] + rpe_bias(table, b, a.Wp, tv);
+          sc[nt][e] = (j0 + jc + nt * 8 + 2 * t + kk < a.Ns) ? v : -INFINITY;
+          mx[r] = fmaxf(mx[r], sc[nt][e]);
+        }
+      }
+      // ---- online softmax (a row lives in the four lanes of a quad)
+      float corr[2];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 1));
+        mx[r] = fmaxf(mx[r], __shfl_xor_sync(0xffffffffu, mx[r], 2));
+        const float mn = fmaxf(m[r], mx[r]);
+        corr[r] = __expf(m[r] - mn);
+        l[r] *= corr[r];
+        m[r] = mn;
+      }
+#pragma unroll
+      for (int nv = 0; nv < KS; ++nv) { o[nv][0] *= corr[0]; o[nv][1] *= corr[0]; o[nv][2] *= corr[1]; o[nv][3] *= corr[1]; }
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          sc[nt][e] = __expf(sc[nt][e] - m[e >> 1]);
+          l[e >> 1] += sc[nt][e];                  // per-lane partial row sum, reduced over the quad at the end
+        }
+      // ---- O += P V; k-step kt = the probabilities of key tile kt, operand columns (t, t+4) = keys (2t, 2t+1)
+#pragma unroll
+      for (int kt = 0; kt < NT; ++kt) {
+        uint32_t ph[4], pl[4];
+        const float pv[4] = {sc[kt][0], sc[kt][2], sc[kt][1], sc[kt][3]};   // a0 (g,2t) a1 (g+8,2t) a2 (g,2t+1) a3 (g+8,2t+1)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ph[e] = tf32_hi(pv[e]);
+          pl[e] = __float_as_uint(pv[e] - __uint_as_float(ph[e]));
+        }
+        uint32_t vh[KS][2], vl[KS][2];
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) {
+          const int off = (jc + kt * 8 + 2 * t) * PAD + nv * 8 + g;  // B[k = t][n = g] = V[key 2t][channel g]; k = t+4: key 2t+1
+          vh[nv][0] = __float_as_uint(sVh[off]); vh[nv][1] = __float_as_uint(sVh[off + PAD]);
+          vl[nv][0] = __float_as_uint(sVl[off]); vl[nv][1] = __float_as_uint(sVl[off + PAD]);
+        }
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(o[nv], ph, vh[nv][0], vh[nv][1]);
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(o[nv], ph, vl[nv][0], vl[nv][1]);
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(o[nv], pl, vh[nv][0], vh[nv][1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 1);
+    l[r] += __shfl_xor_sync(0xffffffffu, l[r], 2);
+  }
+  // accumulator element e of channel tile nv: row (e >> 1), channel nv*8 + 2t + (e & 1)
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int i = iq[r];
+    if (i >= a.Nq) continue;
+    if (a.split == 1) {
+      const float inv = 1.f / l[r];
+#pragma unroll
+      for (int nv = 0; nv < KS; ++nv)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+          a.o_out[((size_t)bh * DH + nv * 8 + 2 * t + kk) * a.Nq + i] = o[nv][2 * r + kk] * inv;
+      if (t == 0) a.o_lse[(size_t)bh * a.Nq + i] = m[r] + logf(l[r]);
+    } else {
+      const size_t pz = (size_t)blockIdx.z * a.BH + bh;
+#pragma unroll
+      for (int nv = 0; nv < KS; ++nv)
+#pragma unroll
+        for (int kk = 0; kk < 2; ++kk)
+          a.part_o[(pz * DH + nv * 8 + 2 * t + kk) * a.Nq + i] = o[nv][2 * r + kk];
+      if (t == 0) {
+        a.part_ml[(pz * 2 + 0) * a.Nq + i] = m[r];
+        a.part_ml[(pz * 2 + 1) * a.Nq + i] = l[r];
+      }
+    }
+  }
+}
+
 // merge the key ranges of the split forward: out = sum_z o_z e^{m_z - m} / sum_z l_z e^{m_z - m}
 template <int DH>
 __global__ void __launch_bounds__(128) rpe_combine_kernel(const __grid_constant__ RpeArgs a) {
@@ -560,6 +774,7 @@ static int pick_split(long long base, int per_sm, int n_tiles, int* tiles_per_sp
   return (n_tiles + tps - 1) / tps;
 }
 static int fwd_split(int BH, int Nq, int Ns, int* tps) {
+  if (K3_FWD_MMA) return pick_split((long long)((Nq + TQM - 1) / TQM) * BH, K3_MMA_MINB, (Ns + TK - 1) / TK, tps);
   return pick_split((long long)((Nq + TQ - 1) / TQ) * BH, FWD_MINB, (Ns + TK - 1) / TK, tps);
 }
 
@@ -589,9 +804,15 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   cudaStream_t st = (cudaStream_t)stream;
   rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, (float*)workspace, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_fwd pad")) return rc;
-  dim3 grid((a.Nq + TQ - 1) / TQ, BH, a.split);
-  if (Dh == 32) rpe_attn_fwd_kernel<32><<<grid, TQ / RQ, 0, st>>>(a);
-  else rpe_attn_fwd_kernel<16><<<grid, TQ / RQ, 0, st>>>(a);
+  if (K3_FWD_MMA) {
+    dim3 grid((a.Nq + TQM - 1) / TQM, BH, a.split);
+    if (Dh == 32) rpe_attn_fwd_mma_kernel<32><<<grid, 128, 0, st>>>(a);
+    else rpe_attn_fwd_mma_kernel<16><<<grid, 128, 0, st>>>(a);
+  } else {
+    dim3 grid((a.Nq + TQ - 1) / TQ, BH, a.split);
+    if (Dh == 32) rpe_attn_fwd_kernel<32><<<grid, TQ / RQ, 0, st>>>(a);
+    else rpe_attn_fwd_kernel<16><<<grid, TQ / RQ, 0, st>>>(a);
+  }
   if (int rc = check_launch("rpe_attn_fwd")) return rc;
   if (a.split > 1) {
     dim3 cgrid((a.Nq + 127) / 128, BH);
