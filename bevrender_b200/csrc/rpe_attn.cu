@@ -341,11 +341,11 @@ __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], 
 // rows [j0, j0+T) of a channel-major (DH, n) matrix as hi[T][PAD] / lo[T][PAD] (zero beyond n)
 template <int T, int DH>
 __device__ __forceinline__ void stage_split(float* __restrict__ hi, float* __restrict__ lo, const float* __restrict__ src,
-                                            int n, int j0) {
+                                            int n, int j0, float mul = 1.f) {
   for (int idx = threadIdx.x; idx < T * DH; idx += blockDim.x) {
     const int c = idx / T, jj = idx - c * T;
     const int j = j0 + jj;
-    const float x = j < n ? __ldg(src + (size_t)c * n + j) : 0.f;
+    const float x = j < n ? __ldg(src + (size_t)c * n + j) * mul : 0.f;
     const float h = __uint_as_float(tf32_hi(x));
     hi[jj * PAD + c] = h;
     lo[jj * PAD + c] = x - h;
@@ -615,6 +615,156 @@ __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const _
   }
 }
 
+// dQ with the three contractions on mma.sync 3xTF32 (same warp tile and staging as rpe_attn_fwd_mma_kernel):
+// S = Q^T K and dP = dO^T V use K / V as the "col" operand indexed (key = g, channel = t); dQ += dS K uses K indexed
+// (key = 2t / 2t+1, channel = g) so that dS is consumed in the accumulator registers it was computed in.
+#ifndef K3_DQ_MMA
+#define K3_DQ_MMA 1
+#endif
+#ifndef K3_DQ_MMA_MINB
+#define K3_DQ_MMA_MINB 3
+#endif
+template <int DH>
+__global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kernel(const __grid_constant__ RpeArgs a) {
+  constexpr int KS = DH / 8, NT = CHM / 8;
+  __shared__ __align__(16) float sKh[TK * PAD], sKl[TK * PAD], sVh[TK * PAD], sVl[TK * PAD];
+  __shared__ __align__(16) float2 sPos[TK];
+  const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int head = bh % a.h, bg = bh / a.hpg;
+  const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
+  const float* kb = a.k + (size_t)bh * DH * a.Ns;
+  const float* vb = a.v + (size_t)bh * DH * a.Ns;
+  const float2* pb = reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns;
+
+  const int i0 = blockIdx.x * TQM + warp * 16;
+  const int iq[2] = {i0 + g, i0 + g + 8};
+  float ay[2], ax[2], lse[2], delta[2];
+  uint32_t qh[KS][4], ql[KS][4], gh[KS][4], gl[KS][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int iy = iq[r] / a.Wq, ixq = iq[r] - iy * a.Wq;
+    ay[r] = rpe_query_half(grid_coord(iy, a.Hq), a.Rh);
+    ax[r] = rpe_query_half(grid_coord(ixq, a.Wq), a.Rw);
+    const bool live = iq[r] < a.Nq;
+    lse[r] = live ? __ldg(a.lse + (size_t)bh * a.Nq + iq[r]) : 0.f;
+    delta[r] = live ? __ldg(a.delta + (size_t)bh * a.Nq + iq[r]) : 0.f;
+  }
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {            // a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
+      const int r = e & 1, c = ks * 8 + t + ((e >> 1) << 2);
+      const size_t idx = ((size_t)bh * DH + c) * a.Nq + iq[r];
+      const float x = iq[r] < a.Nq ? __ldg(a.q + idx) * a.scale : 0.f;
+      const float y = iq[r] < a.Nq ? __ldg(a.grad_out + idx) : 0.f;
+      qh[ks][e] = tf32_hi(x); ql[ks][e] = __float_as_uint(x - __uint_as_float(qh[ks][e]));
+      gh[ks][e] = tf32_hi(y); gl[ks][e] = __float_as_uint(y - __uint_as_float(gh[ks][e]));
+    }
+  float dq[KS][4];
+#pragma unroll
+  for (int nv = 0; nv < KS; ++nv)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) dq[nv][e] = 0.f;
+
+  const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
+  for (int j0 = jbeg; j0 < jend; j0 += TK) {
+    __syncthreads();
+    stage_split<TK, DH>(sKh, sKl, kb, a.Ns, j0);
+    stage_split<TK, DH>(sVh, sVl, vb, a.Ns, j0);
+    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x) {
+      const float2 p = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+      sPos[jj] = make_float2(rpe_key_half(p.x, a.Rh), rpe_key_half(p.y, a.Rw));
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int jc = 0; jc < TK; jc += CHM) {
+      if (j0 + jc >= a.Ns) break;
+      float sc[NT][4], dp[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sc[nt][e] = 0.f; dp[nt][e] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bh_[NT][2], bl_[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int off = (jc + nt * 8 + g) * PAD + ks * 8 + t;
+          bh_[nt][0] = __float_as_uint(sKh[off]); bh_[nt][1] = __float_as_uint(sKh[off + 4]);
+          bl_[nt][0] = __float_as_uint(sKl[off]); bl_[nt][1] = __float_as_uint(sKl[off + 4]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], qh[ks], bh_[nt][0], bh_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], qh[ks], bl_[nt][0], bl_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ql[ks], bh_[nt][0], bh_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int off = (jc + nt * 8 + g) * PAD + ks * 8 + t;
+          bh_[nt][0] = __float_as_uint(sVh[off]); bh_[nt][1] = __float_as_uint(sVh[off + 4]);
+          bl_[nt][0] = __float_as_uint(sVl[off]); bl_[nt][1] = __float_as_uint(sVl[off + 4]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], gh[ks], bh_[nt][0], bh_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], gh[ks], bl_[nt][0], bl_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], gl[ks], bh_[nt][0], bh_[nt][1]);
+      }
+      // dS = P (dP - delta), P = exp(S + bias - lse); element e of tile nt: row (e >> 1), key jc + nt*8 + 2t + (e & 1)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float4 pp = *reinterpret_cast<const float4*>(&sPos[jc + nt * 8 + 2 * t]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1, kk = e & 1;
+          const Bilin b = rpe_taps(ay[r], ax[r], kk ? pp.z : pp.x, kk ? pp.w : pp.y, a.Rh, a.Rw, a.Wp);
+          float tv[4];
+          const float pr = __expf(sc[nt][e] + rpe_bias(table, b, a.Wp, tv) - lse[r]);
+          sc[nt][e] = (j0 + jc + nt * 8 + 2 * t + kk < a.Ns) ? pr * (dp[nt][e] - delta[r]) : 0.f;
+        }
+      }
+      // dQ += dS K; operand columns (t, t+4) = keys (2t, 2t+1)
+#pragma unroll
+      for (int kt = 0; kt < NT; ++kt) {
+        uint32_t ph[4], pl[4];
+        const float pv[4] = {sc[kt][0], sc[kt][2], sc[kt][1], sc[kt][3]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ph[e] = tf32_hi(pv[e]);
+          pl[e] = __float_as_uint(pv[e] - __uint_as_float(ph[e]));
+        }
+        uint32_t kh[KS][2], kl[KS][2];
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) {
+          const int off = (jc + kt * 8 + 2 * t) * PAD + nv * 8 + g;
+          kh[nv][0] = __float_as_uint(sKh[off]); kh[nv][1] = __float_as_uint(sKh[off + PAD]);
+          kl[nv][0] = __float_as_uint(sKl[off]); kl[nv][1] = __float_as_uint(sKl[off + PAD]);
+        }
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(dq[nv], ph, kh[nv][0], kh[nv][1]);
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(dq[nv], ph, kl[nv][0], kl[nv][1]);
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(dq[nv], pl, kh[nv][0], kh[nv][1]);
+      }
+    }
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    if (iq[r] >= a.Nq) continue;
+#pragma unroll
+    for (int nv = 0; nv < KS; ++nv)
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        float* dst = a.grad_q + ((size_t)bh * DH + nv * 8 + 2 * t + kk) * a.Nq + iq[r];
+        if (a.split == 1) *dst = dq[nv][2 * r + kk] * a.scale;
+        else atomicAdd(dst, dq[nv][2 * r + kk] * a.scale);
+      }
+  }
+}
+
 // dK, dV, dpos, drpe: thread = key column, streams Q/dO tiles
 #ifndef K3_TQB
 #define K3_TQB 128
@@ -741,6 +891,218 @@ __global__ void __launch_bounds__(TKB * CS, DKV_MINB) rpe_attn_bwd_dkv_kernel(co
   }
 }
 
+// dK / dV / dpos / drpe with the four contractions on mma.sync 3xTF32.  One warp owns 16 KEYS (the M rows of every tile):
+//   S^T = K Q^T, dP^T = V dO^T   (A = resident K / V fragments, B = staged Q / dO indexed (query = g, channel = t))
+//   dV += P^T dO, dK += dS^T Q   (A = the probabilities / score gradients in their accumulator registers with the
+//                                 (0,2,4,6,1,3,5,7) query order, B = staged dO / Q indexed (query = 2t / 2t+1, channel = g))
+// Element e of score tile nt: key row (e >> 1), query jc + nt*8 + 2t + (e & 1).
+#ifndef K3_DKV_MMA
+#define K3_DKV_MMA 1
+#endif
+#ifndef K3_DKV_MMA_MINB
+#define K3_DKV_MMA_MINB 3
+#endif
+constexpr int TKM = 64;                      // keys per CTA (4 warps x 16)
+
+template <int DH>
+__global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_kernel(const __grid_constant__ RpeArgs a) {
+  constexpr int KS = DH / 8, NT = CHM / 8;
+  __shared__ __align__(16) float sQh[TK * PAD], sQl[TK * PAD], sGh[TK * PAD], sGl[TK * PAD];
+  __shared__ __align__(16) float4 sRow[TK];  // query halves of the bias coordinates (y, x), lse, delta
+  const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  const int head = bh % a.h, bg = bh / a.hpg;
+  const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
+  float* gtable = a.grad_rpe_pad ? a.grad_rpe_pad + ((size_t)((blockIdx.x + blockIdx.y) % a.gcopies) * a.h + head) * a.Hp * a.Wp +
+                                       2 * a.Wp + 2 : nullptr;
+  const float* qb = a.q + (size_t)bh * DH * a.Nq;
+  const float* gb = a.grad_out + (size_t)bh * DH * a.Nq;
+  const bool want_bias_grad = (a.grad_rpe_pad != nullptr) || (a.grad_pos != nullptr);
+
+  const int j0w = blockIdx.x * TKM + warp * 16;
+  const int jk[2] = {j0w + g, j0w + g + 8};
+  float by[2], bx[2], giy[2] = {0.f, 0.f}, gix[2] = {0.f, 0.f};
+  uint32_t kh[KS][4], kl[KS][4], vh[KS][4], vl[KS][4];
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    float2 p = make_float2(0.f, 0.f);
+    if (jk[r] < a.Ns) p = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns + jk[r]);
+    by[r] = rpe_key_half(p.x, a.Rh); bx[r] = rpe_key_half(p.y, a.Rw);
+  }
+#pragma unroll
+  for (int ks = 0; ks < KS; ++ks)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {            // a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
+      const int r = e & 1, c = ks * 8 + t + ((e >> 1) << 2);
+      const size_t idx = ((size_t)bh * DH + c) * a.Ns + jk[r];
+      const float x = jk[r] < a.Ns ? __ldg(a.k + idx) : 0.f;
+      const float y = jk[r] < a.Ns ? __ldg(a.v + idx) : 0.f;
+      kh[ks][e] = tf32_hi(x); kl[ks][e] = __float_as_uint(x - __uint_as_float(kh[ks][e]));
+      vh[ks][e] = tf32_hi(y); vl[ks][e] = __float_as_uint(y - __uint_as_float(vh[ks][e]));
+    }
+  float dk[KS][4], dv[KS][4];
+#pragma unroll
+  for (int nv = 0; nv < KS; ++nv)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { dk[nv][e] = 0.f; dv[nv][e] = 0.f; }
+
+  const int ibeg = blockIdx.z * a.tiles_per_split * TK, iend = min(a.Nq, ibeg + a.tiles_per_split * TK);
+  for (int i0 = ibeg; i0 < iend; i0 += TK) {
+    __syncthreads();
+    stage_split<TK, DH>(sQh, sQl, qb, a.Nq, i0, a.scale);
+    stage_split<TK, DH>(sGh, sGl, gb, a.Nq, i0);
+    for (int ii = threadIdx.x; ii < TK; ii += blockDim.x) {
+      const int i = i0 + ii;
+      float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < a.Nq) {
+        const int iy = i / a.Wq, ixq = i - iy * a.Wq;
+        r = make_float4(rpe_query_half(grid_coord(iy, a.Hq), a.Rh), rpe_query_half(grid_coord(ixq, a.Wq), a.Rw),
+                        __ldg(a.lse + (size_t)bh * a.Nq + i), __ldg(a.delta + (size_t)bh * a.Nq + i));
+      }
+      sRow[ii] = r;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int jc = 0; jc < TK; jc += CHM) {
+      if (i0 + jc >= a.Nq) break;
+      float sc[NT][4], dp[NT][4];
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { sc[nt][e] = 0.f; dp[nt][e] = 0.f; }
+#pragma unroll
+      for (int ks = 0; ks < KS; ++ks) {
+        uint32_t bh_[NT][2], bl_[NT][2];
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int off = (jc + nt * 8 + g) * PAD + ks * 8 + t;
+          bh_[nt][0] = __float_as_uint(sQh[off]); bh_[nt][1] = __float_as_uint(sQh[off + 4]);
+          bl_[nt][0] = __float_as_uint(sQl[off]); bl_[nt][1] = __float_as_uint(sQl[off + 4]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], kh[ks], bh_[nt][0], bh_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], kh[ks], bl_[nt][0], bl_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], kl[ks], bh_[nt][0], bh_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) {
+          const int off = (jc + nt * 8 + g) * PAD + ks * 8 + t;
+          bh_[nt][0] = __float_as_uint(sGh[off]); bh_[nt][1] = __float_as_uint(sGh[off + 4]);
+          bl_[nt][0] = __float_as_uint(sGl[off]); bl_[nt][1] = __float_as_uint(sGl[off + 4]);
+        }
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], vh[ks], bh_[nt][0], bh_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], vh[ks], bl_[nt][0], bl_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], vl[ks], bh_[nt][0], bh_[nt][1]);
+      }
+      // P^T -> sc, dS^T -> dp (in place), bias gradients
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        const float4 r0 = sRow[jc + nt * 8 + 2 * t], r1 = sRow[jc + nt * 8 + 2 * t + 1];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = e >> 1, kk = e & 1;
+          const float4 rq = kk ? r1 : r0;
+          const Bilin b = rpe_taps(rq.x, rq.y, by[r], bx[r], a.Rh, a.Rw, a.Wp);
+          float tv[4];
+          const bool ok = (i0 + jc + nt * 8 + 2 * t + kk < a.Nq) && (jk[r] < a.Ns);
+          const float bias = rpe_bias(table, b, a.Wp, tv);          // always sampled: the taps feed the gradients below
+          const float pr = ok ? __expf(sc[nt][e] + bias - rq.z) : 0.f;
+          const float ds = pr * (dp[nt][e] - rq.w);
+          sc[nt][e] = pr;
+          dp[nt][e] = ds;
+          if (want_bias_grad) {
+            gix[r] = fmaf(ds, b.wy0 * (tv[1] - tv[0]) + b.wy1 * (tv[3] - tv[2]), gix[r]);
+            giy[r] = fmaf(ds, b.wx0 * (tv[2] - tv[0]) + b.wx1 * (tv[3] - tv[1]), giy[r]);
+            if (gtable) {
+              float* g0 = gtable + b.off;
+              float* g1 = g0 + a.Wp;
+              const float dx0 = ds * b.wx0, dx1 = ds * b.wx1;
+              float l0 = dx0 * b.wy0, l1 = dx0 * b.wy1;            // taps (y0, x0), (y0+1, x0)
+              const float r0 = dx1 * b.wy0, r1 = dx1 * b.wy1;      // taps (y0, x0+1), (y0+1, x0+1)
+              // Neighbouring key rows of the tile (lanes 4 apart) sit one table cell apart, so the right-hand taps of
+              // key g+1 are the left-hand taps of key g: hand them over with shuffles and halve the RED sectors.
+              const int off_up = __shfl_down_sync(0xffffffffu, b.off, 4), off_dn = __shfl_up_sync(0xffffffffu, b.off, 4);
+              const float in0 = __shfl_down_sync(0xffffffffu, r0, 4), in1 = __shfl_down_sync(0xffffffffu, r1, 4);
+              if (g < 7 && off_up + 1 == b.off) { l0 += in0; l1 += in1; }
+              atomicAdd(g0, l0); atomicAdd(g1, l1);
+              if (!(g > 0 && b.off + 1 == off_dn)) { atomicAdd(g0 + 1, r0); atomicAdd(g1 + 1, r1); }
+            }
+          }
+        }
+      }
+      // dV += P^T dO, dK += dS^T Q; operand columns (t, t+4) = queries (2t, 2t+1)
+#pragma unroll
+      for (int kt = 0; kt < NT; ++kt) {
+        uint32_t ph[4], pl[4], sh[4], sl[4];
+        const float pv[4] = {sc[kt][0], sc[kt][2], sc[kt][1], sc[kt][3]};
+        const float sv[4] = {dp[kt][0], dp[kt][2], dp[kt][1], dp[kt][3]};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          ph[e] = tf32_hi(pv[e]); pl[e] = __float_as_uint(pv[e] - __uint_as_float(ph[e]));
+          sh[e] = tf32_hi(sv[e]); sl[e] = __float_as_uint(sv[e] - __uint_as_float(sh[e]));
+        }
+        uint32_t xh[KS][2], xl[KS][2];
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) {
+          const int off = (jc + kt * 8 + 2 * t) * PAD + nv * 8 + g;
+          xh[nv][0] = __float_as_uint(sGh[off]); xh[nv][1] = __float_as_uint(sGh[off + PAD]);
+          xl[nv][0] = __float_as_uint(sGl[off]); xl[nv][1] = __float_as_uint(sGl[off + PAD]);
+        }
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(dv[nv], ph, xh[nv][0], xh[nv][1]);
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(dv[nv], ph, xl[nv][0], xl[nv][1]);
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(dv[nv], pl, xh[nv][0], xh[nv][1]);
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) {
+          const int off = (jc + kt * 8 + 2 * t) * PAD + nv * 8 + g;
+          xh[nv][0] = __float_as_uint(sQh[off]); xh[nv][1] = __float_as_uint(sQh[off + PAD]);
+          xl[nv][0] = __float_as_uint(sQl[off]); xl[nv][1] = __float_as_uint(sQl[off + PAD]);
+        }
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(dk[nv], sh, xh[nv][0], xh[nv][1]);
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(dk[nv], sh, xl[nv][0], xl[nv][1]);
+#pragma unroll
+        for (int nv = 0; nv < KS; ++nv) mma_tf32(dk[nv], sl, xh[nv][0], xh[nv][1]);
+      }
+    }
+  }
+  // bias-coordinate gradients of a key row live in the four lanes of a quad
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    giy[r] += __shfl_xor_sync(0xffffffffu, giy[r], 1); giy[r] += __shfl_xor_sync(0xffffffffu, giy[r], 2);
+    gix[r] += __shfl_xor_sync(0xffffffffu, gix[r], 1); gix[r] += __shfl_xor_sync(0xffffffffu, gix[r], 2);
+  }
+#pragma unroll
+  for (int r = 0; r < 2; ++r) {
+    const int j = jk[r];
+    if (j >= a.Ns) continue;
+#pragma unroll
+    for (int nv = 0; nv < KS; ++nv)
+#pragma unroll
+      for (int kk = 0; kk < 2; ++kk) {
+        const size_t idx = ((size_t)bh * DH + nv * 8 + 2 * t + kk) * a.Ns + j;
+        if (a.split == 1) {
+          if (a.grad_k) a.grad_k[idx] = dk[nv][2 * r + kk];      // the staged Q carries `scale`
+          if (a.grad_v) a.grad_v[idx] = dv[nv][2 * r + kk];
+        } else {
+          if (a.grad_k) atomicAdd(a.grad_k + idx, dk[nv][2 * r + kk]);
+          if (a.grad_v) atomicAdd(a.grad_v + idx, dv[nv][2 * r + kk]);
+        }
+      }
+    if (a.grad_pos && t == 0) {
+      float* gp = a.grad_pos + ((size_t)bg * a.Ns + j) * 2;
+      atomicAdd(gp, giy[r] * (-0.25f * (float)(a.Rh - 1)));
+      atomicAdd(gp + 1, gix[r] * (-0.25f * (float)(a.Rw - 1)));
+    }
+  }
+}
+
 static int validate(int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw) {
   BEVR_REQUIRE(Dh == 32 || Dh == 16, "rpe_attn: only Dh == 32 and Dh == 16 are built (got %d)", Dh);
   BEVR_REQUIRE(BH > 0 && h > 0 && hpg > 0 && BH % h == 0 && h % hpg == 0, "rpe_attn: bad BH=%d h=%d hpg=%d", BH, h, hpg);
@@ -850,22 +1212,35 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   else rpe_delta_kernel<16><<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
   if (int rc = check_launch("rpe_attn_bwd delta")) return rc;
   if (grad_q) {
-    const int nqt = (a.Nq + TQ - 1) / TQ;
-    a.split = pick_split((long long)nqt * BH, K3_DQ_MINB, (Ns + TK - 1) / TK, &a.tiles_per_split);
+    const int tq = K3_DQ_MMA ? TQM : TQ;
+    const int nqt = (a.Nq + tq - 1) / tq;
+    a.split = pick_split((long long)nqt * BH, K3_DQ_MMA ? K3_DQ_MMA_MINB : K3_DQ_MINB, (Ns + TK - 1) / TK, &a.tiles_per_split);
     if (a.split > 1) cudaMemsetAsync(grad_q, 0, (size_t)BH * Dh * a.Nq * sizeof(float), st);
-    if (Dh == 32) rpe_attn_bwd_dq_kernel<32><<<dim3(nqt, BH, a.split), TQ, 0, st>>>(a);
-    else rpe_attn_bwd_dq_kernel<16><<<dim3(nqt, BH, a.split), TQ, 0, st>>>(a);
+    if (K3_DQ_MMA) {
+      if (Dh == 32) rpe_attn_bwd_dq_mma_kernel<32><<<dim3(nqt, BH, a.split), 128, 0, st>>>(a);
+      else rpe_attn_bwd_dq_mma_kernel<16><<<dim3(nqt, BH, a.split), 128, 0, st>>>(a);
+    } else {
+      if (Dh == 32) rpe_attn_bwd_dq_kernel<32><<<dim3(nqt, BH, a.split), TQ, 0, st>>>(a);
+      else rpe_attn_bwd_dq_kernel<16><<<dim3(nqt, BH, a.split), TQ, 0, st>>>(a);
+    }
     if (int rc = check_launch("rpe_attn_bwd dq")) return rc;
   }
   if (grad_k || grad_v || grad_rpe || grad_pos) {
-    const int nkt = (Ns + TKB - 1) / TKB;
-    a.split = pick_split((long long)nkt * BH, DKV_MINB < 2 ? 2 : DKV_MINB, (a.Nq + TQB - 1) / TQB, &a.tiles_per_split);
+    const int nkt = K3_DKV_MMA ? (Ns + TKM - 1) / TKM : (Ns + TKB - 1) / TKB;
+    const int nqt = K3_DKV_MMA ? (a.Nq + TK - 1) / TK : (a.Nq + TQB - 1) / TQB;
+    const int per_sm = K3_DKV_MMA ? K3_DKV_MMA_MINB : (DKV_MINB < 2 ? 2 : DKV_MINB);
+    a.split = pick_split((long long)nkt * BH, per_sm, nqt, &a.tiles_per_split);
     if (a.split > 1) {
       if (grad_k) cudaMemsetAsync(grad_k, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
       if (grad_v) cudaMemsetAsync(grad_v, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
     }
-    if (Dh == 32) rpe_attn_bwd_dkv_kernel<32><<<dim3(nkt, BH, a.split), TKB * CS, 0, st>>>(a);
-    else rpe_attn_bwd_dkv_kernel<16><<<dim3(nkt, BH, a.split), TKB * CS, 0, st>>>(a);
+    if (K3_DKV_MMA) {
+      if (Dh == 32) rpe_attn_bwd_dkv_mma_kernel<32><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a);
+      else rpe_attn_bwd_dkv_mma_kernel<16><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a);
+    } else {
+      if (Dh == 32) rpe_attn_bwd_dkv_kernel<32><<<dim3(nkt, BH, a.split), TKB * CS, 0, st>>>(a);
+      else rpe_attn_bwd_dkv_kernel<16><<<dim3(nkt, BH, a.split), TKB * CS, 0, st>>>(a);
+    }
     if (int rc = check_launch("rpe_attn_bwd dkv")) return rc;
   }
   if (grad_rpe) {
