@@ -25,6 +25,9 @@ struct RpeArgs {
   // so every kernel also cuts its STREAMED dimension into `split` ranges of `tiles_per_split` tiles.
   int split, tiles_per_split;
   float *part_o, *part_ml;   // forward partials: (split, BH, DH, Nq) unnormalised outputs, (split, BH, 2, Nq) max / sum
+  // mma kernels: operands pre-split into tf32 hi / lo parts, row-major (BH, n rounded up to 64, DH), zero rows beyond n
+  const float *kh, *kl, *vh, *vl, *qh, *ql, *gh, *gl;
+  int NsP, NqP;
   float scale;
 };
 
@@ -352,6 +355,40 @@ __device__ __forceinline__ void stage_split(float* __restrict__ hi, float* __res
   }
 }
 
+// One pass per operand instead of one per (CTA, tile): x (BH, DH, n) channel-major -> hi / lo (BH, nP, DH) row-major.
+// Every CTA used to transpose, round and split its K / V (Q / dO) tiles itself -- a fifth of the mma kernels' instructions.
+template <int DH>
+__global__ void __launch_bounds__(256) rpe_presplit_kernel(const float* __restrict__ x, float* __restrict__ hi,
+                                                           float* __restrict__ lo, int n, int nP, float mul) {
+  const int bh = blockIdx.y, j = blockIdx.x * 64 + (threadIdx.x & 63), c0 = (threadIdx.x >> 6) * (DH / 4);
+  if (j >= nP) return;
+  float h[DH / 4], l[DH / 4];
+#pragma unroll
+  for (int c = 0; c < DH / 4; ++c) {
+    const float v = j < n ? __ldg(x + ((size_t)bh * DH + c0 + c) * n + j) * mul : 0.f;
+    h[c] = __uint_as_float(tf32_hi(v));
+    l[c] = v - h[c];
+  }
+  float4* dh = reinterpret_cast<float4*>(hi + ((size_t)bh * nP + j) * DH + c0);
+  float4* dl = reinterpret_cast<float4*>(lo + ((size_t)bh * nP + j) * DH + c0);
+#pragma unroll
+  for (int c = 0; c < DH / 16; ++c) {
+    dh[c] = make_float4(h[4 * c], h[4 * c + 1], h[4 * c + 2], h[4 * c + 3]);
+    dl[c] = make_float4(l[4 * c], l[4 * c + 1], l[4 * c + 2], l[4 * c + 3]);
+  }
+}
+// 64 rows of a pre-split operand -> shared memory [64][PAD] with 16-byte async copies (LDGSTS)
+template <int DH>
+__device__ __forceinline__ void stage_async(float* __restrict__ dst, const float* __restrict__ src_tile) {
+  constexpr int CPR = DH / 4;                // 16-byte chunks per row
+  for (int idx = threadIdx.x; idx < TK * CPR; idx += blockDim.x) {
+    const int row = idx / CPR, ch = idx - row * CPR;
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst + row * PAD + ch * 4);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src_tile + row * DH + ch * 4) : "memory");
+  }
+}
+__device__ __forceinline__ void stage_async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
+
 template <int DH>
 __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(const __grid_constant__ RpeArgs a) {
   constexpr int KS = DH / 8;                 // k-steps of S = Q^T K (channels) = n-tiles of O (channels)
@@ -393,12 +430,16 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
   const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
   for (int j0 = jbeg; j0 < jend; j0 += TK) {
     __syncthreads();
-    stage_split<TK, DH>(sKh, sKl, kb, a.Ns, j0);
-    stage_split<TK, DH>(sVh, sVl, vb, a.Ns, j0);
+    {
+      const size_t tile = ((size_t)bh * a.NsP + j0) * DH;
+      stage_async<DH>(sKh, a.kh + tile); stage_async<DH>(sKl, a.kl + tile);
+      stage_async<DH>(sVh, a.vh + tile); stage_async<DH>(sVl, a.vl + tile);
+    }
     for (int jj = threadIdx.x; jj < TK; jj += blockDim.x) {
       const float2 p = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
       sPos[jj] = make_float2(rpe_key_half(p.x, a.Rh), rpe_key_half(p.y, a.Rw));
     }
+    stage_async_wait();
     __syncthreads();
 #pragma unroll 1
     for (int jc = 0; jc < TK; jc += CHM) {
@@ -669,12 +710,16 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
   const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
   for (int j0 = jbeg; j0 < jend; j0 += TK) {
     __syncthreads();
-    stage_split<TK, DH>(sKh, sKl, kb, a.Ns, j0);
-    stage_split<TK, DH>(sVh, sVl, vb, a.Ns, j0);
+    {
+      const size_t tile = ((size_t)bh * a.NsP + j0) * DH;
+      stage_async<DH>(sKh, a.kh + tile); stage_async<DH>(sKl, a.kl + tile);
+      stage_async<DH>(sVh, a.vh + tile); stage_async<DH>(sVl, a.vl + tile);
+    }
     for (int jj = threadIdx.x; jj < TK; jj += blockDim.x) {
       const float2 p = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
       sPos[jj] = make_float2(rpe_key_half(p.x, a.Rh), rpe_key_half(p.y, a.Rw));
     }
+    stage_async_wait();
     __syncthreads();
 #pragma unroll 1
     for (int jc = 0; jc < TK; jc += CHM) {
@@ -948,8 +993,11 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
   const int ibeg = blockIdx.z * a.tiles_per_split * TK, iend = min(a.Nq, ibeg + a.tiles_per_split * TK);
   for (int i0 = ibeg; i0 < iend; i0 += TK) {
     __syncthreads();
-    stage_split<TK, DH>(sQh, sQl, qb, a.Nq, i0, a.scale);
-    stage_split<TK, DH>(sGh, sGl, gb, a.Nq, i0);
+    {
+      const size_t tile = ((size_t)bh * a.NqP + i0) * DH;
+      stage_async<DH>(sQh, a.qh + tile); stage_async<DH>(sQl, a.ql + tile);
+      stage_async<DH>(sGh, a.gh + tile); stage_async<DH>(sGl, a.gl + tile);
+    }
     for (int ii = threadIdx.x; ii < TK; ii += blockDim.x) {
       const int i = i0 + ii;
       float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -960,6 +1008,7 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
       }
       sRow[ii] = r;
     }
+    stage_async_wait();
     __syncthreads();
 #pragma unroll 1
     for (int jc = 0; jc < TK; jc += CHM) {
@@ -1140,6 +1189,10 @@ static int fwd_split(int BH, int Nq, int Ns, int* tps) {
   return pick_split((long long)((Nq + TQ - 1) / TQ) * BH, FWD_MINB, (Ns + TK - 1) / TK, tps);
 }
 
+static size_t round64(int n) { return ((size_t)n + 63) / 64 * 64; }
+
+// workspace layout (floats): [padded table][backward: gcopies padded gradient tables][forward: key-range partials]
+//                            [K hi, K lo, V hi, V lo : BH * NsP * Dh each][backward: Q hi, Q lo, dO hi, dO lo : BH * NqP * Dh each]
 extern "C" size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward) {
   size_t n = pad_floats(h, Rh, Rw) * (backward ? 1 + grad_copies(h, Rh, Rw) : 1);
   if (!backward) {
@@ -1147,7 +1200,27 @@ extern "C" size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, i
     const int ks = fwd_split(BH, Nq, Ns, &tps);
     if (ks > 1) n += (size_t)ks * BH * (Dh + 2) * Nq;
   }
-  return n * sizeof(float);
+  n += 4 * (size_t)BH * round64(Ns) * Dh;
+  if (backward) n += 4 * (size_t)BH * round64(Nq) * Dh;
+  return n * sizeof(float) + 256;          // slack: the pre-split operands start on a 256-byte boundary
+}
+
+template <int DH>
+static int presplit(const float* x, float* hi, float* lo, int BH, int n, int nP, float mul, cudaStream_t st) {
+  rpe_presplit_kernel<DH><<<dim3(nP / 64, BH), 256, 0, st>>>(x, hi, lo, n, nP, mul);
+  return check_launch("rpe_attn presplit");
+}
+// K and V of a call -> hi / lo row-major copies at `base`; returns the first float after them
+static float* presplit_kv(RpeArgs& a, const float* k, const float* v, float* base, int Dh, cudaStream_t st, int* rc) {
+  base = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(base) + 255) & ~(uintptr_t)255);   // 16-byte async copies
+  a.NsP = (int)round64(a.Ns);
+  const size_t n = (size_t)a.BH * a.NsP * Dh;
+  float *kh = base, *kl = base + n, *vh = base + 2 * n, *vl = base + 3 * n;
+  a.kh = kh; a.kl = kl; a.vh = vh; a.vl = vl;
+  *rc = Dh == 32 ? presplit<32>(k, kh, kl, a.BH, a.Ns, a.NsP, 1.f, st) : presplit<16>(k, kh, kl, a.BH, a.Ns, a.NsP, 1.f, st);
+  if (*rc) return nullptr;
+  *rc = Dh == 32 ? presplit<32>(v, vh, vl, a.BH, a.Ns, a.NsP, 1.f, st) : presplit<16>(v, vh, vl, a.BH, a.Ns, a.NsP, 1.f, st);
+  return base + 4 * n;
 }
 
 extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
@@ -1166,6 +1239,11 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   cudaStream_t st = (cudaStream_t)stream;
   rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, (float*)workspace, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_fwd pad")) return rc;
+  if (K3_FWD_MMA) {
+    int rc = 0;
+    presplit_kv(a, k, v, a.part_o + (a.split > 1 ? (size_t)a.split * BH * (Dh + 2) * a.Nq : 0), Dh, st, &rc);
+    if (rc) return rc;
+  }
   if (K3_FWD_MMA) {
     dim3 grid((a.Nq + TQM - 1) / TQM, BH, a.split);
     if (Dh == 32) rpe_attn_fwd_mma_kernel<32><<<grid, 128, 0, st>>>(a);
@@ -1208,6 +1286,20 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, pad, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_bwd pad")) return rc;
   if (grad_rpe) cudaMemsetAsync(gpad, 0, pad_floats(h, Rh, Rw) * sizeof(float) * a.gcopies, st);
+  if (K3_DQ_MMA || K3_DKV_MMA) {
+    int rc = 0;
+    float* nxt = presplit_kv(a, k, v, gpad + pad_floats(h, Rh, Rw) * a.gcopies, Dh, st, &rc);
+    if (rc) return rc;
+    a.NqP = (int)round64(a.Nq);
+    const size_t n = (size_t)BH * a.NqP * Dh;
+    float *qh = nxt, *ql = nxt + n, *gh = nxt + 2 * n, *gl = nxt + 3 * n;
+    a.qh = qh; a.ql = ql; a.gh = gh; a.gl = gl;
+    rc = Dh == 32 ? presplit<32>(q, qh, ql, BH, a.Nq, a.NqP, scale, st) : presplit<16>(q, qh, ql, BH, a.Nq, a.NqP, scale, st);
+    if (rc) return rc;
+    rc = Dh == 32 ? presplit<32>(grad_out, gh, gl, BH, a.Nq, a.NqP, 1.f, st)
+                  : presplit<16>(grad_out, gh, gl, BH, a.Nq, a.NqP, 1.f, st);
+    if (rc) return rc;
+  }
   if (Dh == 32) rpe_delta_kernel<32><<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
   else rpe_delta_kernel<16><<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
   if (int rc = check_launch("rpe_attn_bwd delta")) return rc;

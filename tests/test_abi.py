@@ -92,12 +92,15 @@ def test_offset_head_validation_and_empty_batch():
 
 
 def test_rpe_attention_workspace_covers_the_forward_split():
-    """The forward's key-range partials live in the caller's workspace: the size query must grow with B*h*Nq when the
-    grid is small enough to be split, and not for large grids."""
+    """The forward's key-range partials and the pre-split tf32 operands live in the caller's workspace: the size query
+    must cover the padded table, the partials when the grid is small enough to be split, and 4 operand copies."""
     from bevrender_b200 import _lib
     L = _lib.lib()
     table = 2 * (111 + 4) * (111 + 4) * 4
+    kv = 4 * 16 * 3136 * 32 * 4                            # K/V hi/lo, Ns = 3136 is a multiple of 64
     small = L.bevr_rpe_attn_workspace_bytes(16, 2, 32, 3136, 3136, 111, 111, 0)
-    assert small > table + 16 * 34 * 3136 * 4            # at least two ranges of (Dh + 2) floats per row
+    assert small > table + kv + 16 * 34 * 3136 * 4         # at least two ranges of (Dh + 2) floats per row
     big = L.bevr_rpe_attn_workspace_bytes(8, 8, 32, 40000, 40000, 399, 399, 0)
-    assert big == 8 * 403 * 403 * 4                       # 2504 CTAs already: no split, padded table only
+    assert big == 8 * 403 * 403 * 4 + 4 * 8 * 40000 * 32 * 4 + 256      # 5000 CTAs already: no split
+    bwd = L.bevr_rpe_attn_workspace_bytes(8, 8, 32, 40000, 40000, 399, 399, 1)
+    assert bwd >= 8 * 403 * 403 * 4 * 2 + 8 * 8 * 40000 * 32 * 4       # + Q / dO copies and >= 1 gradient table
