@@ -27,6 +27,7 @@ SIGNATURES = {
     "bevr_correlate_workspace_bytes": (_z, [_i] * 6),
     "bevr_correlate": (_i, [_p] * 5 + [_i] * 6 + [_p]),
     "bevr_rpe_attn_workspace_bytes": (_z, [_i] * 8),
+    "bevr_rpe_attn_set_mma": (None, [_i]),
     "bevr_rpe_attn_fwd": (_i, [_p] * 8 + [_i] * 9 + [_f, _p]),
     "bevr_rpe_attn_bwd": (_i, [_p] * 15 + [_i] * 9 + [_f, _p]),
     "bevr_offset_head_fwd": (_i, [_p] * 5 + [C.c_longlong, _p, _p] + [_i] * 7 + [_f, _f, _p]),

@@ -11,6 +11,7 @@
 // All arithmetic is fp32 FFMA on the CUDA cores (the 1e-4 tolerance rules out tf32/bf16 tensor
 // cores; Dh = 32 is small).
 #include <math.h>
+#include <stdlib.h>
 
 #include "bevr_common.cuh"
 
@@ -1184,8 +1185,19 @@ static int pick_split(long long base, int per_sm, int n_tiles, int* tiles_per_sp
   *tiles_per_split = tps;
   return (n_tiles + tps - 1) / tps;
 }
+// Which kernel family serves a call: the mma.sync kernels win from the reference-native shape (56x56) upwards; at very
+// small grids (28x28: 0.6 M (query, key) pairs per head) their fixed costs (operand pre-split launches, fragment loads of
+// 2-tile CTAs) lose to the FFMA2 kernels.  BEVR_K3_MMA=0/1 forces one family (benchmarks, tests).
+static int g_k3_mma = -1;     // -1 auto, 0 FFMA2 kernels, 1 mma.sync kernels (bevr_rpe_attn_set_mma, tuning / test hook)
+static bool use_mma(int Nq, int Ns) {
+  static const int env = [] { const char* e = getenv("BEVR_K3_MMA"); return e ? atoi(e) : -1; }();
+  const int forced = g_k3_mma >= 0 ? g_k3_mma : env;
+  if (forced >= 0) return forced != 0;
+  return (long long)Nq * Ns >= (3ll << 20);
+}
+
 static int fwd_split(int BH, int Nq, int Ns, int* tps) {
-  if (K3_FWD_MMA) return pick_split((long long)((Nq + TQM - 1) / TQM) * BH, K3_MMA_MINB, (Ns + TK - 1) / TK, tps);
+  if (K3_FWD_MMA && use_mma(Nq, Ns)) return pick_split((long long)((Nq + TQM - 1) / TQM) * BH, K3_MMA_MINB, (Ns + TK - 1) / TK, tps);
   return pick_split((long long)((Nq + TQ - 1) / TQ) * BH, FWD_MINB, (Ns + TK - 1) / TK, tps);
 }
 
@@ -1193,6 +1205,8 @@ static size_t round64(int n) { return ((size_t)n + 63) / 64 * 64; }
 
 // workspace layout (floats): [padded table][backward: gcopies padded gradient tables][forward: key-range partials]
 //                            [K hi, K lo, V hi, V lo : BH * NsP * Dh each][backward: Q hi, Q lo, dO hi, dO lo : BH * NqP * Dh each]
+extern "C" void bevr_rpe_attn_set_mma(int mode) { g_k3_mma = mode; }
+
 extern "C" size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward) {
   size_t n = pad_floats(h, Rh, Rw) * (backward ? 1 + grad_copies(h, Rh, Rw) : 1);
   if (!backward) {
@@ -1239,12 +1253,13 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   cudaStream_t st = (cudaStream_t)stream;
   rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, (float*)workspace, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_fwd pad")) return rc;
-  if (K3_FWD_MMA) {
+  const bool mma = K3_FWD_MMA && use_mma(a.Nq, Ns);
+  if (mma) {
     int rc = 0;
     presplit_kv(a, k, v, a.part_o + (a.split > 1 ? (size_t)a.split * BH * (Dh + 2) * a.Nq : 0), Dh, st, &rc);
     if (rc) return rc;
   }
-  if (K3_FWD_MMA) {
+  if (mma) {
     dim3 grid((a.Nq + TQM - 1) / TQM, BH, a.split);
     if (Dh == 32) rpe_attn_fwd_mma_kernel<32><<<grid, 128, 0, st>>>(a);
     else rpe_attn_fwd_mma_kernel<16><<<grid, 128, 0, st>>>(a);
@@ -1286,7 +1301,8 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, pad, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_bwd pad")) return rc;
   if (grad_rpe) cudaMemsetAsync(gpad, 0, pad_floats(h, Rh, Rw) * sizeof(float) * a.gcopies, st);
-  if (K3_DQ_MMA || K3_DKV_MMA) {
+  const bool mma_dq = K3_DQ_MMA && use_mma(a.Nq, Ns), mma_dkv = K3_DKV_MMA && use_mma(a.Nq, Ns);
+  if (mma_dq || mma_dkv) {
     int rc = 0;
     float* nxt = presplit_kv(a, k, v, gpad + pad_floats(h, Rh, Rw) * a.gcopies, Dh, st, &rc);
     if (rc) return rc;
@@ -1304,11 +1320,11 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   else rpe_delta_kernel<16><<<dim3((a.Nq + 255) / 256, BH), 256, 0, st>>>(a);
   if (int rc = check_launch("rpe_attn_bwd delta")) return rc;
   if (grad_q) {
-    const int tq = K3_DQ_MMA ? TQM : TQ;
+    const int tq = mma_dq ? TQM : TQ;
     const int nqt = (a.Nq + tq - 1) / tq;
-    a.split = pick_split((long long)nqt * BH, K3_DQ_MMA ? K3_DQ_MMA_MINB : K3_DQ_MINB, (Ns + TK - 1) / TK, &a.tiles_per_split);
+    a.split = pick_split((long long)nqt * BH, mma_dq ? K3_DQ_MMA_MINB : K3_DQ_MINB, (Ns + TK - 1) / TK, &a.tiles_per_split);
     if (a.split > 1) cudaMemsetAsync(grad_q, 0, (size_t)BH * Dh * a.Nq * sizeof(float), st);
-    if (K3_DQ_MMA) {
+    if (mma_dq) {
       if (Dh == 32) rpe_attn_bwd_dq_mma_kernel<32><<<dim3(nqt, BH, a.split), 128, 0, st>>>(a);
       else rpe_attn_bwd_dq_mma_kernel<16><<<dim3(nqt, BH, a.split), 128, 0, st>>>(a);
     } else {
@@ -1318,15 +1334,15 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
     if (int rc = check_launch("rpe_attn_bwd dq")) return rc;
   }
   if (grad_k || grad_v || grad_rpe || grad_pos) {
-    const int nkt = K3_DKV_MMA ? (Ns + TKM - 1) / TKM : (Ns + TKB - 1) / TKB;
-    const int nqt = K3_DKV_MMA ? (a.Nq + TK - 1) / TK : (a.Nq + TQB - 1) / TQB;
-    const int per_sm = K3_DKV_MMA ? K3_DKV_MMA_MINB : (DKV_MINB < 2 ? 2 : DKV_MINB);
+    const int nkt = mma_dkv ? (Ns + TKM - 1) / TKM : (Ns + TKB - 1) / TKB;
+    const int nqt = mma_dkv ? (a.Nq + TK - 1) / TK : (a.Nq + TQB - 1) / TQB;
+    const int per_sm = mma_dkv ? K3_DKV_MMA_MINB : (DKV_MINB < 2 ? 2 : DKV_MINB);
     a.split = pick_split((long long)nkt * BH, per_sm, nqt, &a.tiles_per_split);
     if (a.split > 1) {
       if (grad_k) cudaMemsetAsync(grad_k, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
       if (grad_v) cudaMemsetAsync(grad_v, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
     }
-    if (K3_DKV_MMA) {
+    if (mma_dkv) {
       if (Dh == 32) rpe_attn_bwd_dkv_mma_kernel<32><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a);
       else rpe_attn_bwd_dkv_mma_kernel<16><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a);
     } else {

@@ -120,6 +120,10 @@ int bevr_project_points(const float* points, const float* cam_T, const float* K,
  * Requires Dh == 32 (the reference uses 32 channels per head everywhere, encoder.py:23-39) or Dh == 16.
  */
 size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward);
+/* Tuning / test hook (process-wide, not thread-safe): which K3 kernel family serves the calls that follow.
+ * -1 (default) picks by problem size, 0 = FFMA2 kernels, 1 = mma.sync 3xTF32 kernels.  Call it between a
+ * workspace-size query and the launch it sizes, and the two disagree -- set it first. */
+void bevr_rpe_attn_set_mma(int mode);
 int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe,
                       const float* pos, float* out, float* lse, void* workspace, int BH, int h,
                       int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw, float scale,

@@ -8,6 +8,16 @@ from util import FP32_TOL, rel_err
 pytestmark = pytest.mark.gpu
 
 
+@pytest.fixture(params=[0, 1], ids=["ffma2", "mma"], autouse=True)
+def kernel_family(request):
+    """Every case runs on both K3 kernel families (the default picks by problem size: small grids would only ever
+    exercise the FFMA2 kernels, the reference-native and larger ones only the mma.sync 3xTF32 kernels)."""
+    from bevrender_b200 import _lib
+    _lib.lib().bevr_rpe_attn_set_mma(request.param)
+    yield request.param
+    _lib.lib().bevr_rpe_attn_set_mma(-1)
+
+
 def _case(B, h, g, Hq, Wq, Hk, Wk, Rw_mul, seed, spread, Dh=32):
     torch.manual_seed(seed)
     Nq, Ns = Hq * Wq, Hk * Wk
