@@ -115,8 +115,12 @@ int bevr_project_points(const float* points, const float* cam_T, const float* K,
  *   out      dev f32 (BH, Dh, Nq)
  *   lse      dev f32 (BH, Nq)         log-sum-exp per row (saved for backward)
  *   hpg      heads per group (head bh uses pos[bh / hpg], table rpe[bh % h])
- *   workspace dev, bevr_rpe_attn_workspace_bytes(BH, h, Dh, Nq, Ns, Rh, Rw, backward) bytes: holds the zero-padded
- *            copy of the table the kernels sample (and, for backward, its padded gradient)
+ *   workspace dev, bevr_rpe_attn_workspace_bytes(BH, h, Dh, Nq, Ns, Rh, Rw, backward) bytes: the zero-padded
+ *            copy of the table the kernels sample, the forward's key-range partials (small grids are split
+ *            over key ranges), the tf32 hi/lo copies of K, V (and Q, dO for backward) that the mma.sync
+ *            kernels stage from, and, for backward, the privatised padded table gradients
+ * The contractions run as mma.sync.m16n8k8 TF32 with a hi/lo operand split (3 products, fp32 accumulate:
+ * fp32-grade results); grids below ~40x40 are served by an FFMA2 kernel family (see bevr_rpe_attn_set_mma).
  * Requires Dh == 32 (the reference uses 32 channels per head everywhere, encoder.py:23-39) or Dh == 16.
  */
 size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward);
