@@ -4,12 +4,21 @@
 //                                bias = grid_sample(rpe_table, (qgrid_i - pos_j)/2)        :264-305
 //                                out  = softmax_j(attn + bias) v^T                          :308-330
 // (same code at SCA_deform_attn.py:331-411).  The reference materialises attn, bias and the
-// displacement tensor at (Nq, Ns); here nothing of size Nq*Ns ever exists: one thread owns one
-// query row (forward, dQ) or one key column (dK/dV/dpos/drpe), K/V (resp. Q/dO) tiles are staged
-// in shared memory and broadcast to the warp, the bias is a bilinear lookup computed on the fly
-// from the query index and the staged key position, and the softmax is the online (flash) form.
-// All arithmetic is fp32 FFMA on the CUDA cores (the 1e-4 tolerance rules out tf32/bf16 tensor
-// cores; Dh = 32 is small).
+// displacement tensor at (Nq, Ns); here nothing of size Nq*Ns ever exists: K/V (resp. Q/dO) tiles are
+// staged in shared memory, the bias is a bilinear lookup computed on the fly from the query index and
+// the staged key position, the softmax is the online (flash) form, and the backward recomputes.
+//
+// Two kernel families (DESIGN.md section "K3"), picked per call by problem size (use_mma):
+//   * mma.sync 3xTF32 -- rpe_attn_fwd_mma_kernel, rpe_attn_bwd_dq_mma_kernel, rpe_attn_bwd_dkv_mma_kernel:
+//     one warp owns 16 query rows (or 16 keys); the contractions run on the legacy warp-level tensor-core
+//     instruction with a hi/lo operand split that keeps fp32-grade accuracy (a single TF32 product would
+//     not hold the 1e-4 budget); bias lookup and softmax stay on the CUDA cores.  Operands are pre-split
+//     once per call (rpe_presplit_kernel) and staged with cp.async.
+//   * FFMA2 -- rpe_attn_fwd_kernel, rpe_attn_bwd_dq_kernel, rpe_attn_bwd_dkv_kernel: one thread owns one
+//     query row or key column, tiles broadcast from shared memory; serves grids below ~40x40.
+// Shared by both: the zero-padded table copy (rpe_pad_kernel), the hoisted bias coordinates, the split of the
+// streamed dimension over blockIdx.z (rpe_combine_kernel merges the forward's key ranges) and the privatised
+// table-gradient copies (rpe_unpad_add_kernel).
 #include <math.h>
 #include <stdlib.h>
 
