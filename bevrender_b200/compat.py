@@ -6,10 +6,34 @@ replaces the three symbols the callers look up at construction time:
 and ``model.bevrender.BEV2CameraProjector`` (bevrender.py:11,31).
 """
 import importlib
+import os
 import sys
 import types
 
 import torch
+
+_ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def find_reference():
+    """Directory holding the reference's ``model/`` package: ``$BEVR_REFERENCE``, the authoring container's
+    ``/root/reference``, or the staged copy that travels to the GPU box (``oracle/_ref/reference``, written by
+    ``make -C oracle``).  Returns None when none exists."""
+    for cand in (os.environ.get("BEVR_REFERENCE"), "/root/reference", os.path.join(_ROOT, "oracle", "_ref", "reference")):
+        if cand and os.path.isdir(os.path.join(cand, "model")):
+            return cand
+    return None
+
+
+def add_reference_to_path():
+    """Make ``import model.encoder`` (the reference's caller of the hot path) resolvable; raises if there is no checkout."""
+    ref = find_reference()
+    if ref is None:
+        raise ImportError("no reference checkout found (BEVR_REFERENCE, /root/reference, oracle/_ref/reference)")
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    ensure_timm_stub()
+    return ref
 
 
 def ensure_timm_stub():

@@ -149,6 +149,30 @@ def test_full_size_properties():
     assert rel_err(o1[:, band].cpu(), ref) < FP32_TOL
 
 
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16], ids=["fp32", "bf16"])
+def test_full_size_backward_vs_oracle(dtype):
+    """BASELINE.json config 2 at full size (B = 1): out, grad_value, grad_loc and grad_weight of the whole sample
+    against the oracle (evaluated with CUDA torch on the box -- the same grid_sample construction, fp32), plus three
+    query bands checked element-wise.  bf16: storage dtype bf16, oracle in fp32 on the rounded inputs."""
+    from util import assert_close
+    d = make_microbench_inputs(1, seed=2)
+    tol = FP32_TOL if dtype == torch.float32 else BF16_TOL
+    out, gv, gl, gw = _run_cuda(d, dtype, False, False)
+    cast = lambda t: t.to(dtype).float().cuda()
+    ref = omsda.msda_forward_backward(cast(d["value"]), d["spatial_shapes"], d["level_start_index"],
+                                      d["sampling_locations"].cuda(), cast(d["attention_weights"]), cast(d["grad_out"]))
+    for n, a, b in zip(("out", "grad_value", "grad_loc", "grad_weight"), (out, gv, gl, gw), ref):
+        e = rel_err(a.float(), b)
+        assert e < tol, f"{n}: rel err {e:.3e} >= {tol}"
+    if dtype == torch.float32:
+        for r0 in (0, 97, 184):                       # first rows (level borders), middle, last rows
+            band = slice(r0 * 200, (r0 + 16) * 200)
+            assert_close(out[:, band], ref[0][:, band], tol, f"out rows {r0}")
+            assert_close(gl[:, band], ref[2][:, band], tol, f"grad_loc rows {r0}")
+            assert_close(gw[:, band], ref[3][:, band], tol, f"grad_weight rows {r0}")
+        assert_close(gv, ref[1], tol, "grad_value")
+
+
 def test_host_pipeline_matches_device_path():
     """The pinned-host entry point (chunked H2D / compute / D2H pipeline) returns what the device path returns."""
     import bevrender_b200 as bb

@@ -1,0 +1,230 @@
+"""Parity against the REAL reference at BASELINE sizes, on the GPU box.
+
+``make -C oracle`` stages the unmodified reference checkout under ``oracle/_ref/reference`` (git-ignored, travels
+with the gpurun snapshot).  These tests run the reference's own modules (``model/TSA_deform_attn.py``,
+``model/SCA_deform_attn.py``, ``model/encoder.py``, ``model/bevrender.py``) with CUDA torch (fp32, TF32 off) and the
+B200 drop-ins on identical seeded inputs and state_dicts:
+
+  * module level at N = 28, 50 (BASELINE config 1) and 56 (reference-native), out + every gradient, with the K3
+    kernel family left on *auto* (N=28 -> FFMA2 family, N>=50 -> mma family, key/query splits as the host picks them);
+  * the reference's ``EncoderLayer`` (encoder.py:243-411) built twice -- as shipped and under
+    ``compat.install(wrappers=True)`` -- at N = 50, forward + backward;
+  * the unmodified ``BEVRender`` (bevrender.py:14-221; backbone + 2 encoder layers + render decoder, window of 3
+    frames incl. the eval-mode history passes and the history-BEV warp) against the same model with the drop-ins.
+Tolerances: 1e-4 of max|ref| (north_star) plus the element-wise check of tests/util.py; the multi-layer model test
+states its own (error compounds through BatchNorm / LayerNorm stacks).
+"""
+import copy
+
+import numpy as np
+import pytest
+import torch
+
+from bevrender_b200 import compat, workloads
+from util import FP32_TOL, assert_close, rel_err
+
+pytestmark = [pytest.mark.gpu,
+              pytest.mark.skipif(compat.find_reference() is None, reason="no reference checkout (make -C oracle)")]
+
+
+@pytest.fixture(autouse=True)
+def _fp32_library_math():
+    old = (torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32)
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
+
+
+def _reference_classes():
+    """The reference's own classes, looked up BEFORE compat.install() rebinds the names."""
+    compat.add_reference_to_path()
+    import importlib
+    tsa = importlib.import_module("model.TSA_deform_attn").TSADeformableAttention
+    sca = importlib.import_module("model.SCA_deform_attn").SCADeformableAttention
+    proj = importlib.import_module("model.bev_cmr_proj").BEV2CameraProjector
+    return tsa, sca, proj
+
+
+def _stress(module, gen, gain):
+    """rpe_table ~ N(0, 0.5^2) and larger offsets so the bias path and the zero-padding branches matter."""
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if name.endswith("rpe_table"):
+                p.copy_(torch.randn(p.shape, generator=gen).to(p.device) * 0.5)
+            if "conv_offset" in name and name.endswith(".3.weight"):
+                p.mul_(gain)
+
+
+def _compare_param_grads(ours, ref, tol=FP32_TOL):
+    ref_g = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
+    our_p = dict(ours.named_parameters())
+    scale = max(float(g.abs().max()) for g in ref_g.values())
+    for k, g in ref_g.items():
+        got = our_p[k].grad
+        assert got is not None, k
+        if float(g.abs().max()) < 1e-5 * scale:          # mathematically zero gradients (key bias): rounding noise
+            assert float(got.abs().max()) < 1e-5 * scale, k
+            continue
+        assert_close(got, g, tol, "grad " + k)
+    for k, p in our_p.items():
+        if k not in ref_g:
+            assert p.grad is None, k
+
+
+@pytest.mark.parametrize("N,B,k,s", [(28, 2, 3, 1), (50, 1, 3, 1), (56, 2, 3, 1), (56, 2, 9, 8)])
+def test_tsa_module_vs_reference_on_box(N, B, k, s):
+    import bevrender_b200 as bb
+    RefTSA, _, _ = _reference_classes()
+    torch.manual_seed(N)
+    gen = torch.Generator().manual_seed(N + 1)
+    kw = dict(bev_feat_shape=N, dim_embed=64, n_heads=2, n_groups=1, stride=s, kernel_size=k, scale_offset_range=True,
+              batch_size=B, n_views=1)
+    ref = RefTSA(**kw).cuda()
+    _stress(ref, gen, 8.0)
+    ours = bb.TSADeformableAttention(**kw).cuda()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    q0 = torch.randn(B, 64, N, N, generator=gen).cuda()
+    x0 = torch.randn(B, 64, N, N, generator=gen).cuda()
+    go = torch.randn(B, 64, N, N, generator=gen).cuda()
+    res = []
+    for m in (ref, ours):
+        q, x = q0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        out, _ = m(x, q, {}, False)
+        out.backward(go)
+        res.append((out.detach(), q.grad, x.grad))
+    for name, a, b in zip(("out", "grad_query", "grad_x"), res[1], res[0]):
+        assert_close(a, b, FP32_TOL, f"TSA N={N} {name}")
+    _compare_param_grads(ours, ref)
+
+
+def _reference_points(N, D, B, RefProj):
+    """Projected reference points exactly as SpatialCrossAttn builds them (SCA.py:38-40,78-85) with the reference's
+    own projector: (B, 1, N/2, N*D, 2)."""
+    import importlib
+    T, K = workloads.default_camera()
+    proj = RefProj(imu_to_rgb={0: [T]}, K={0: [K.copy()]}, vehicle_type_code=0, img_width=160, img_height=128,
+                   ori_img_width=640, ori_img_height=512, device="cpu")
+    SCA = importlib.import_module("model.SCA").SpatialCrossAttn
+    holder = SCA.__new__(SCA)                              # only sample_3d_points() is needed: no module construction
+    holder.bev_bound, holder.bev_feat_shape, holder.bev_depth_dim, holder.z_shift = {"X": 20.0, "Y": 10.0, "Z": 2.0}, N, D, -1.0
+    pts = SCA.sample_3d_points(holder)
+    uv = torch.stack(proj.bev_grid_to_camera(pts)[0], 0)                       # (V, 2, N/2, N, D)
+    V, _, hh, ww, dd = uv.shape
+    return uv.permute(0, 2, 3, 4, 1).reshape(1, V, hh, ww * dd, 2).repeat(B, 1, 1, 1, 1)
+
+
+@pytest.mark.parametrize("N,B,D", [(28, 2, 5), (50, 1, 5), (56, 2, 5)])
+def test_sca_module_vs_reference_on_box(N, B, D):
+    import bevrender_b200 as bb
+    _, RefSCA, RefProj = _reference_classes()
+    torch.manual_seed(100 + N)
+    gen = torch.Generator().manual_seed(N + 7)
+    kw = dict(bev_feat_shape=N, bev_depth_dim=D, dim_embed=64, n_heads=2, n_groups=1, stride=1, kernel_size=1,
+              scale_offset_range=True, batch_size=B, n_views=1)
+    ref = RefSCA(**kw).cuda()
+    _stress(ref, gen, 4.0)
+    ours = bb.SCADeformableAttention(**kw).cuda()
+    ours.load_state_dict(ref.state_dict(), strict=True)
+    pts = _reference_points(N, D, B, RefProj).cuda()
+    q0 = torch.randn(B, 64, N, N, generator=gen).cuda()
+    x0 = torch.randn(B, 1, 64, 32, 40, generator=gen).cuda()
+    go = torch.randn(B, 64, N, N, generator=gen).cuda()
+    res = []
+    for m in (ref, ours):
+        q, x = q0.clone().requires_grad_(True), x0.clone().requires_grad_(True)
+        out, _ = m(x, q, pts, {}, False)
+        out.backward(go)
+        res.append((out.detach(), q.grad, x.grad))
+    for name, a, b in zip(("out", "grad_query", "grad_x"), res[1], res[0]):
+        assert_close(a, b, FP32_TOL, f"SCA N={N} {name}")
+    _compare_param_grads(ours, ref)
+
+
+def _encoder_layer_pair(N, B):
+    """The reference EncoderLayer as shipped, and the same class constructed under compat.install(wrappers=True)."""
+    import importlib
+    _, _, RefProj = _reference_classes()
+    enc = importlib.import_module("model.encoder")
+    tsa_mod, sca_mod = importlib.import_module("model.TSA"), importlib.import_module("model.SCA")
+    saved = (tsa_mod.TSADeformableAttention, sca_mod.SCADeformableAttention, enc.SpatialCrossAttn, enc.TemporalSelfAttn)
+    T, K = workloads.default_camera()
+    mk_proj = lambda cls, **kw: cls(imu_to_rgb={0: [T]}, K={0: [K.copy()]}, vehicle_type_code=0, img_width=160,
+                                    img_height=128, ori_img_width=640, ori_img_height=512, **kw)
+    kw = dict(bev_bound={"X": 20.0, "Y": 10.0, "Z": 2.0}, n_views=1, bev_feat_shape=N, bev_depth_dim=5, z_shift=-1.0,
+              dim_embed=64, expansion=2, stage_idx=0, n_groups=1, n_heads=2, stride=1, kernel_size=3, batch_size=B,
+              scale_offset_range=True, drop_path_rate=0.0)
+    torch.manual_seed(0)
+    ref_layer = enc.EncoderLayer(bev2cmr_projector=mk_proj(RefProj, device="cpu"), **kw)
+    try:
+        import bevrender_b200 as bb
+        compat.install(wrappers=True)
+        new_layer = enc.EncoderLayer(bev2cmr_projector=mk_proj(bb.BEV2CameraProjector), **kw)
+    finally:
+        tsa_mod.TSADeformableAttention, sca_mod.SCADeformableAttention, enc.SpatialCrossAttn, enc.TemporalSelfAttn = saved
+    return ref_layer, new_layer
+
+
+def test_encoder_layer_config1_vs_reference_on_box():
+    """BASELINE config 1 shape: N = 50, C = 64, 2 heads, D = 5, image features 32x40, B = 1, prev_bev given."""
+    N, B = 50, 1
+    ref_layer, new_layer = _encoder_layer_pair(N, B)
+    gen = torch.Generator().manual_seed(3)
+    _stress(ref_layer, gen, 6.0)
+    new_layer.load_state_dict(ref_layer.state_dict(), strict=True)
+    ref_layer, new_layer = ref_layer.cuda().train(), new_layer.cuda().train()
+    q0 = torch.randn(B, 64, N, N, generator=gen).cuda()
+    img0 = torch.randn(B, 64, 32, 40, generator=gen).cuda()
+    prev = torch.randn(B, 64, N, N, generator=gen).cuda()
+    go = torch.randn(B, 64, N, N, generator=gen).cuda()
+    veh = torch.tensor(0)
+    res = []
+    for layer in (ref_layer, new_layer):
+        q, img = q0.clone().requires_grad_(True), img0.clone().requires_grad_(True)
+        out, _ = layer(bev_query=q, img_tensor=img, prev_bev=prev, vehicle_pose=None, vehicle_type_idx=veh,
+                       wandb_log_dict={}, return_wandb_log=False)
+        out.backward(go)
+        res.append((out.detach(), q.grad, img.grad))
+    for name, a, b in zip(("out", "grad_query", "grad_img"), res[1], res[0]):
+        assert_close(a, b, FP32_TOL, f"EncoderLayer N={N} {name}")
+    _compare_param_grads(new_layer, ref_layer)
+
+
+def test_bevrender_model_with_dropins_vs_reference_on_box():
+    """The unmodified BEVRender (ResNet18 backbone, 2 encoder layers at bev 28, render decoder; window of 3 frames =
+    2 eval-mode history passes incl. the history-BEV warp + 1 training pass) with and without the drop-ins."""
+    import importlib
+    _reference_classes()
+    top = importlib.import_module("model.bevrender")
+    enc = importlib.import_module("model.encoder")
+    tsa_mod, sca_mod = importlib.import_module("model.TSA"), importlib.import_module("model.SCA")
+    saved = (tsa_mod.TSADeformableAttention, sca_mod.SCADeformableAttention, enc.SpatialCrossAttn, enc.TemporalSelfAttn,
+             top.BEV2CameraProjector)
+    B = 2
+    cfg = workloads.bevrender_config(bev=28, layers=2, batch=B)
+    torch.manual_seed(0)
+    ref_model = top.BEVRender(copy.deepcopy(cfg), None, "train")
+    try:
+        compat.install(wrappers=True)
+        new_model = top.BEVRender(copy.deepcopy(cfg), None, "train")
+    finally:
+        (tsa_mod.TSADeformableAttention, sca_mod.SCADeformableAttention, enc.SpatialCrossAttn, enc.TemporalSelfAttn,
+         top.BEV2CameraProjector) = saved
+    gen = torch.Generator().manual_seed(5)
+    _stress(ref_model, gen, 4.0)
+    new_model.load_state_dict(ref_model.state_dict(), strict=True)
+    ref_model, new_model = ref_model.cuda(), new_model.cuda()
+    cam, pose, veh, target = workloads.make_train_batch(B, window=3, seed=1)
+    cam, pose, veh, target = cam.cuda(), pose.cuda(), veh.cuda(), target.cuda()
+    outs = []
+    for m in (ref_model, new_model):
+        out, _ = m(cam, pose, veh, {}, True)
+        torch.nn.functional.mse_loss(out, target).backward()
+        outs.append(out.detach())
+    # error compounds through 3 passes x 2 layers + BatchNorm decoder: 5x the single-module budget
+    assert rel_err(outs[1], outs[0]) < 5 * FP32_TOL
+    ref_g = {k: p.grad for k, p in ref_model.named_parameters() if p.grad is not None}
+    new_p = dict(new_model.named_parameters())
+    worst = max((rel_err(new_p[k].grad, g), k) for k, g in ref_g.items() if float(g.abs().max()) > 1e-7)
+    assert worst[0] < 2e-3, f"worst parameter gradient {worst}"
+    assert {k for k, p in new_p.items() if p.grad is not None} == set(ref_g)

@@ -99,3 +99,26 @@ def test_rpe_attention_masked_reference_points():
     assert rel_err(out.cpu(), ref) < FP32_TOL
     for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, cpu):
         assert rel_err(a.grad.cpu(), b.grad) < FP32_TOL, name
+
+
+def test_rpe_attention_n100_backward_vs_dense_oracle_on_device():
+    """N = 100 (Nq = Ns = 10^4, split == 1 paths): all five gradients against the dense oracle, which at this size
+    (0.8 GB attention matrix per tensor) is evaluated with CUDA torch on the box (fp32 library math, TF32 off)."""
+    import bevrender_b200 as bb
+    from util import assert_close
+    old = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        B, h, N = 1, 2, 100
+        q, k, v, rpe, pos, go = _case(B, h, 1, N, N, N, N, 1, 11, 0.01)
+        ref_in = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+        ref = oda.rpe_attention_dense(*ref_in, N, N, 1, 32 ** -0.5)
+        ref.backward(go.cuda())
+        dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+        out = bb.rpe_attention(*dev, N, N, 1)
+        out.backward(go.cuda())
+        assert_close(out, ref.detach(), FP32_TOL, "out")
+        for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, ref_in):
+            assert_close(a.grad, b.grad, FP32_TOL, "grad_" + name)
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = old

@@ -26,3 +26,22 @@ def rel_err(a, b):
 
 FP32_TOL = 1e-4     # north_star: "within 1e-4 relative in fp32"
 BF16_TOL = 1e-2     # north_star: "1e-2 in bf16"
+
+
+def elementwise_violation(a, b, rtol=1e-3, atol_frac=2e-5):
+    """Element-wise companion of ``rel_err`` (a global-max norm lets a small-magnitude element be 100 % wrong):
+    the largest value of |a-b| / (rtol*|b| + atol_frac*max|b|) over the tensor; <= 1 means every element is
+    within ``rtol`` of its own reference value, up to an absolute floor of ``atol_frac`` of the tensor's scale
+    (fp32 sums of O(10^3..10^4) terms accumulated in a different order -- atomics, split-K -- differ by about that)."""
+    a = torch.as_tensor(a).detach().double()
+    b = torch.as_tensor(b).detach().double()
+    floor = atol_frac * b.abs().max().clamp_min(1e-30)
+    return float(((a - b).abs() / (rtol * b.abs() + floor)).max())
+
+
+def assert_close(a, b, tol=FP32_TOL, what="", rtol=1e-3, atol_frac=2e-5):
+    """Both norms: global max-norm error < tol (north_star) AND no element outside rtol/atol."""
+    e = rel_err(a, b)
+    assert e < tol, f"{what}: max-norm rel err {e:.3e} >= {tol}"
+    v = elementwise_violation(a, b, rtol, atol_frac)
+    assert v <= 1.0, f"{what}: element-wise check violated by {v:.2f}x (rtol={rtol}, atol={atol_frac}*max|ref|)"
