@@ -5,7 +5,11 @@
 
 A "step" is one forward + backward pass of the multi-scale deformable-attention gather over one
 batch of B=8 synthetic samples per GPU (200x200 BEV queries, 4 levels, 8 heads, 4 points, Dh=32),
-through the C ABI of libbevr.so.  Prints ONE JSON line (see DESIGN.md "Measurement").
+through the C ABI of libbevr.so.  Prints ONE JSON line (see DESIGN.md "Measurement").  The same line
+carries, as extra objects, the config-5 training step of the reference BEVRender with the drop-ins
+("train": samples/s with the NCCL gradient allreduce and SyncBatchNorm inside the timed region, every
+rank), and on single-GPU runs K3 alone ("k3"), the correlation ("k5") and config 1 against the real
+reference on the host cores ("config1").
 """
 import argparse
 import ctypes as C
@@ -187,11 +191,228 @@ def workload_config(B, dtype):
             "no explicit flush", "parallelism": "batch-sharded, no data-path collective"}
 
 
+def timeit_cuda(fn, warm=3, iters=10):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def build_train_model(B, bev, layers, dev):
+    """BASELINE.json config 5 model: the UNMODIFIED reference ``BEVRender`` (model/bevrender.py:14-221: ResNet18 backbone,
+    1 stage x `layers` EncoderLayers, render decoder) constructed under ``compat.install(wrappers=True)``, i.e. with the
+    drop-in attention modules / projector / wrappers of this repo behind the reference's own encoder.py.  The reference
+    checkout is found at /root/reference or, on the GPU box, at oracle/_ref/reference (staged by ``make -C oracle``).
+    Falls back to the stand-in harness (labelled) only when no checkout exists."""
+    from bevrender_b200 import compat, workloads
+    if compat.find_reference() is None:
+        from bevrender_b200.harness import BevHarness
+        m = BevHarness(n=bev, c=64, heads=2, depth=5, layers=layers, batch=B, device=dev)
+        return m, "stand-in harness (no reference checkout on this box)", lambda cam, pose, veh: m(cam[:, :, 0])
+    compat.add_reference_to_path()
+    compat.install(wrappers=True)
+    from model.bevrender import BEVRender
+    m = BEVRender(workloads.bevrender_config(bev=bev, layers=layers, batch=B), None, "train")
+    return m, "reference BEVRender (model/bevrender.py, unmodified) + compat.install(wrappers=True)", \
+        lambda cam, pose, veh: m(cam, pose, veh, {}, True)[0]
+
+
+def train_leg(args, dev, rank, world, steps, warmup):
+    """One training step of config 5, batch-data-parallel: H2D of the batch -> forward (window of 4 frames: 3 history
+    passes in eval mode without gradient + 1 training pass, bevrender.py:124-146) -> MSE render loss + plain-torch
+    contrastive + triplet losses on the flattened outputs -> backward with the flat-bucket NCCL gradient allreduce
+    overlapped (dp.FlatGradAllReduce, replaces DDP train.py:133-135) -> clip_grad_norm_(1.0) -> AdamW
+    (train.py:236-247, 706-711).  BatchNorm layers are converted to SyncBatchNorm when world > 1, as train.py:129-131."""
+    import torch.distributed as dist
+    from bevrender_b200 import losses, workloads
+    from bevrender_b200.dp import FlatGradAllReduce, find_live_parameters
+    B, T, bev, layers = args.batch, 4, args.bev, 6
+    tf32 = torch.backends.cudnn.allow_tf32
+    torch.backends.cudnn.allow_tf32 = True            # the reference's own convolutions: torch defaults
+    torch.manual_seed(0)
+    model, label, fwd = build_train_model(B, bev, layers, dev)
+    n_bn = sum(isinstance(m, torch.nn.modules.batchnorm._BatchNorm) for m in model.modules())
+    if world > 1:
+        model = torch.nn.SyncBatchNorm.convert_sync_batchnorm(model)
+    model = model.to(dev).train()
+    cam, pose, veh, target = workloads.make_train_batch(B, window=T, seed=1 + rank)
+    h_in = [t.pin_memory() for t in (cam, pose, veh, target)]
+    h_loss = torch.zeros(1).pin_memory()
+
+    def loss_of(cam_d, pose_d, veh_d, target_d):
+        out = fwd(cam_d, pose_d, veh_d)
+        return (torch.nn.functional.mse_loss(out, target_d) + losses.contrastive_loss(out, target_d) +
+                losses.triplet_loss(out, target_d))
+
+    d0 = [t.to(dev) for t in h_in]
+    live_named = find_live_parameters(model, lambda: loss_of(*d0).backward())
+    live = [p for _, p in live_named]
+    live_ids = {id(p) for p in live}
+    n_dead = 0
+    for p in model.parameters():
+        if id(p) not in live_ids:
+            p.requires_grad_(False)
+            n_dead += 1
+    opt = torch.optim.AdamW(live, lr=1e-4, weight_decay=1e-2, eps=1e-8)
+    red = FlatGradAllReduce(live, n_buckets=2)
+
+    def step():
+        cam_d, pose_d, veh_d, target_d = (t.to(dev, non_blocking=True) for t in h_in)
+        red.reset()
+        loss = loss_of(cam_d, pose_d, veh_d, target_d)
+        loss.backward()
+        red.finish()
+        torch.nn.utils.clip_grad_norm_(live, 1.0)
+        opt.step()
+        h_loss.copy_(loss.detach().reshape(1), non_blocking=True)
+
+    for _ in range(warmup):
+        step()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    ms /= steps
+    torch.backends.cudnn.allow_tf32 = tf32
+    nparam = sum(p.numel() for p in live)
+    red.remove()
+    return {"samples_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "steps": steps, "warmup": warmup,
+            "nranks": world, "batch_per_gpu": B, "allreduce_bytes": nparam * 4, "allreduce_launches_per_step": len(red.buckets),
+            "sync_batchnorm": world > 1, "batchnorm_layers": n_bn, "live_params": nparam, "excluded_param_tensors": n_dead,
+            "loss": float(h_loss), "h2d_bytes_per_step": sum(t.numel() * t.element_size() for t in h_in),
+            "model": label, "config": "config5: bev %d, 1 stage x %d layers, window %d, image 128x160, C=64, 2 heads, D=5; "
+            "loss = MSE + contrastive + triplet (plain torch, bevrender_b200/losses.py)" % (bev, layers, T)}
+
+
+def k3_leg():
+    """K3 (fused attention with sampled RPE bias) alone, at the reference-native shapes of config 3(i): N=56, C=64, 2 heads,
+    B=8 -> BH=16; TSA keys 56x56, SCA keys 28x280 (D=5).  Forward and full backward (all five gradients) in ms,
+    (query, key) pairs/s -- SURVEY.md section 8(d): K3 is reported as achieved gathers/s, one bilinear gather per pair."""
+    import bevrender_b200 as bb
+    res = {}
+    for name, Hk, Wk, mul in (("tsa", 56, 56, 1), ("sca", 28, 280, 5)):
+        torch.manual_seed(0)
+        BH, Dh, N = 16, 32, 56
+        Nq, Ns = N * N, Hk * Wk
+        mk = lambda *s: torch.randn(*s, device="cuda")
+        q, k, v = mk(BH, Dh, Nq).requires_grad_(True), mk(BH, Dh, Ns).requires_grad_(True), mk(BH, Dh, Ns).requires_grad_(True)
+        rpe = (mk(2, 2 * N - 1, 2 * N * mul - 1) * 0.5).requires_grad_(True)
+        ys = torch.linspace(-1, 1, Hk, device="cuda")
+        xs = torch.linspace(-1, 1, Wk, device="cuda")
+        pos = torch.stack(torch.meshgrid(ys, xs, indexing="ij"), -1).reshape(1, Ns, 2).repeat(8, 1, 1)
+        pos = (pos + 0.02 * mk(8, Ns, 2)).requires_grad_(True)
+        go = mk(BH, Dh, Nq)
+        f = lambda: bb.rpe_attention(q, k, v, rpe, pos, N, N, 1)
+        t_f = timeit_cuda(f)
+
+        def fb():
+            for t in (q, k, v, rpe, pos):
+                t.grad = None
+            f().backward(go)
+        t_fb = timeit_cuda(fb)
+        pairs = BH * Nq * Ns
+        res[name] = {"fwd_ms": t_f, "bwd_ms": t_fb - t_f, "pairs": pairs, "fwd_pairs_per_s": pairs / (t_f * 1e-3),
+                     "fwd_bwd_pairs_per_s": pairs / (t_fb * 1e-3)}
+    res["shape"] = "N=56, C=64, 2 heads, B=8 (BH=16), Dh=32; TSA Ns=3136, SCA Ns=7840 (D=5)"
+    return res
+
+
+def k5_leg():
+    """K5 (rotation-sweep correlation, tcgen05) at config 4: template (3,224,224) vs map (3,512,512), 72 rotations."""
+    import math
+    import bevrender_b200 as bb
+    R, Ht, Hm, C = 72, 224, 512, 3
+    ang = [2 * math.pi * r / R for r in range(R)]
+    torch.manual_seed(0)
+    m, t = torch.randn(C, Hm, Hm, device="cuda"), torch.randn(C, Ht, Ht, device="cuda")
+    ms = timeit_cuda(lambda: bb.correlate(m, t, ang), 3, 5)
+    flops = 2.0 * (Hm - Ht + 1) ** 2 * R * C * Ht * Ht
+    try:
+        peak = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["bf16_tflops_sustained"])
+        src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)"
+    except Exception:
+        peak, src = 1324.9, "fallback 1324.9 TFLOP/s"
+    return {"ms": ms, "useful_TFLOPs": flops / ms / 1e9, "peak_TFLOPs": peak, "frac": flops / ms / 1e9 / peak,
+            "peak_source": src, "bound": "tensor", "config": "config4: C=3, 224x224 template, 512x512 map, 72 rotations"}
+
+
+def config1_leg(cores):
+    """BASELINE.json config 1, the reference's own CPU-runnable case: ONE reference ``EncoderLayer`` (encoder.py:243-411;
+    N=50, C=64, 2 heads, D=5, image features 32x40, B=1, prev_bev given), forward + backward.  The real reference runs on
+    the box's host cores (kind='reference'); the same layer class built under compat.install() runs on the GPU."""
+    import copy
+    import importlib
+    from bevrender_b200 import compat, workloads
+    if compat.find_reference() is None:
+        return {"unavailable": "no reference checkout on this box"}
+    compat.add_reference_to_path()
+    import bevrender_b200 as bb
+    enc = importlib.import_module("model.encoder")
+    tsa_mod, sca_mod = importlib.import_module("model.TSA"), importlib.import_module("model.SCA")
+    RefProj = importlib.import_module("model.bev_cmr_proj").BEV2CameraProjector
+    saved = (tsa_mod.TSADeformableAttention, sca_mod.SCADeformableAttention, enc.SpatialCrossAttn, enc.TemporalSelfAttn)
+    N, B = 50, 1
+    T, K = workloads.default_camera()
+    pk = dict(imu_to_rgb={0: [T]}, vehicle_type_code=0, img_width=160, img_height=128, ori_img_width=640, ori_img_height=512)
+    kw = dict(bev_bound={"X": 20.0, "Y": 10.0, "Z": 2.0}, n_views=1, bev_feat_shape=N, bev_depth_dim=5, z_shift=-1.0,
+              dim_embed=64, expansion=2, stage_idx=0, n_groups=1, n_heads=2, stride=1, kernel_size=3, batch_size=B,
+              scale_offset_range=True, drop_path_rate=0.0)
+    torch.manual_seed(0)
+    try:
+        if type(saved[0]).__module__.startswith("bevrender_b200") or saved[0].__module__.startswith("bevrender_b200"):
+            importlib.reload(tsa_mod), importlib.reload(sca_mod), importlib.reload(enc)   # undo an earlier install()
+        ref_layer = enc.EncoderLayer(bev2cmr_projector=RefProj(K={0: [K.copy()]}, device="cpu", **pk), **kw)
+        compat.install(wrappers=True)
+        new_layer = enc.EncoderLayer(bev2cmr_projector=bb.BEV2CameraProjector(K={0: [K.copy()]}, **pk), **kw)
+    finally:
+        tsa_mod.TSADeformableAttention, sca_mod.SCADeformableAttention, enc.SpatialCrossAttn, enc.TemporalSelfAttn = saved
+    new_layer.load_state_dict(ref_layer.state_dict(), strict=True)
+    new_layer = new_layer.cuda().train()
+    ref_layer.train()
+    g = torch.Generator().manual_seed(3)
+    q0, img0, prev, go = (torch.randn(*s, generator=g) for s in ((B, 64, N, N), (B, 64, 32, 40), (B, 64, N, N), (B, 64, N, N)))
+
+    def run(layer, dev):
+        q, img = q0.to(dev).requires_grad_(True), img0.to(dev).requires_grad_(True)
+        out, _ = layer(bev_query=q, img_tensor=img, prev_bev=prev.to(dev), vehicle_pose=None, vehicle_type_idx=torch.tensor(0),
+                       wandb_log_dict={}, return_wandb_log=False)
+        out.backward(go.to(dev))
+        return out
+    torch.set_num_threads(cores)
+    run(ref_layer, "cpu")
+    ts = []
+    for _ in range(2):
+        t0 = time.perf_counter()
+        run(ref_layer, "cpu")
+        ts.append(time.perf_counter() - t0)
+    gpu_ms = timeit_cuda(lambda: run(new_layer, "cuda"), 3, 10)
+    return {"workload": "config1: reference EncoderLayer fwd+bwd, N=50, C=64, 2 heads, D=5, img feat 32x40, B=1",
+            "reference_cpu_ms": min(ts) * 1e3, "cores": cores, "kind": "reference", "ours_gpu_ms": gpu_ms,
+            "speedup": min(ts) * 1e3 / gpu_ms, "queries": N * N,
+            "note": "GPU time includes the host->device copies of the inputs and the layer's PyTorch glue (launch-bound at B=1)"}
+
+
 def run_train(args):
-    """--workload train (BASELINE.json config 5): end-to-end training step of the caller-side harness
-    (stem -> 6 x [TSA, SCA] encoder layers with the drop-in modules -> render head; MSE loss, AdamW, clip 1.0;
-    window of 4 frames = 3 history passes without gradient + 1 pass with gradient), batch-data-parallel with the
-    flat-bucket NCCL gradient allreduce.  Metric: training samples/s, whole job."""
+    """--workload train: the config-5 training step alone, as its own JSON line (the contract line carries the same numbers
+    under "train")."""
     import torch.distributed as dist
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -200,64 +421,17 @@ def run_train(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    from bevrender_b200.dp import FlatGradAllReduce, live_named_parameters
-    from bevrender_b200.harness import BevHarness
-    torch.backends.cudnn.allow_tf32 = True           # the PyTorch convolutions of the harness, as torch defaults
-    torch.manual_seed(0)
-    B, T, n = args.batch, 4, args.bev
-    model = BevHarness(n=n, c=64, heads=2, depth=5, layers=6, batch=B, device=dev).to(dev)
-    live = [p for _, p in live_named_parameters(model)]
-    for name, p in model.named_parameters():
-        if all(p is not q for q in live):
-            p.requires_grad_(False)
-    opt = torch.optim.AdamW(live, lr=1e-4, weight_decay=1e-2)
-    red = FlatGradAllReduce(live, n_buckets=2)
-    g = torch.Generator().manual_seed(1 + rank)
-    frames_h = torch.rand(B, T, 3, 128, 160, generator=g).pin_memory()
-    target_h = torch.rand(B, 3, 224, 224, generator=g).pin_memory()
-
-    def step():
-        frames = frames_h.to(dev, non_blocking=True)
-        target = target_h.to(dev, non_blocking=True)
-        red.reset()
-        loss = torch.nn.functional.mse_loss(model(frames), target)
-        loss.backward()
-        red.finish()
-        torch.nn.utils.clip_grad_norm_(live, 1.0)
-        opt.step()
-        return loss
-
-    for _ in range(max(args.warmup, 3)):
-        step()
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with ClockSampler(local) as clk:
-        e0.record()
-        for _ in range(args.steps):
-            loss = step()
-        e1.record()
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
-    ms /= args.steps
+        tr = train_leg(args, dev, rank, world, args.steps, max(args.warmup, 3))
     if rank == 0:
-        nparam = sum(p.numel() for p in live)
-        emit({"metric": "train samples/s", "value": world * B / (ms * 1e-3), "unit": "samples/s",
-                          "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms,
-                          "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-                          "data": "synthetic", "loss": float(loss.detach()),
-                          "config": {"workload": "config5: harness training step, bev %d, 6 layers, window 4, "
-                                     "image 128x160, C=64, 2 heads, D=5" % n, "batch_per_gpu": B,
-                                     "parallelism": "dp%d, flat fp32 gradient bucket (%d params, %.1f MB), 2 NCCL "
-                                     "allreduce(AVG) launches overlapped with backward" % (world, nparam, nparam * 4 / 1e6)},
-                          "clocks": clk.summary()})
+        emit({"metric": "train samples/s", "value": tr["samples_per_s"], "unit": "samples/s", "n_gpus": world,
+              "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": tr["ms_per_step"], "higher_is_better": True,
+              "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+              "config": {"workload": tr["config"], "model": tr["model"], "batch_per_gpu": args.batch,
+                         "parallelism": "dp%d, flat fp32 gradient bucket (%.1f MB, %d NCCL allreduce(AVG) launches overlapped "
+                         "with backward), SyncBatchNorm=%s" % (world, tr["allreduce_bytes"] / 1e6,
+                                                                tr["allreduce_launches_per_step"], tr["sync_batchnorm"])},
+              "train": tr, "clocks": clk.summary()})
     if world > 1:
         dist.destroy_process_group()
 
@@ -273,7 +447,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer leg")
-    ap.add_argument("--tile", default="", help="tuning: tile_w,tile_h,threads")
+    ap.add_argument("--no-train", action="store_true", help="skip the config-5 training-step leg")
+    ap.add_argument("--no-extra", action="store_true", help="skip the K3 / K5 / config-1 legs")
     ap.add_argument("--workload", default="msda", choices=["msda", "train"],
                     help="msda = BASELINE config 2 (the contract line); train = config 5 harness training step")
     ap.add_argument("--bev", type=int, default=56, help="--workload train: BEV grid size")
@@ -298,9 +473,6 @@ def main():
     from bevrender_b200 import _lib
     from bevrender_b200.workloads import make_microbench_inputs
     L = _lib.lib()
-    if args.tile:
-        tw, th, thr = [int(v) for v in args.tile.split(",")]
-        L.bevr_msda_set_tile(tw, th, thr)
     B = args.batch
     tdt = torch.float32 if args.dtype == "fp32" else torch.bfloat16
     dt = 0 if args.dtype == "fp32" else 1
@@ -379,16 +551,22 @@ def main():
     t_bwd = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
     ab_fwd, ab_bwd = algorithmic_bytes(B, esize)
     peak, peak_src = peaks()
-    dom = ("msda_bwd_kernel", ab_bwd, t_bwd) if t_bwd >= t_fwd else ("msda_fwd_kernel", ab_fwd, t_fwd)
+    bwd_name = "msda_bwd_sorted_kernel"
+    dom = (bwd_name, ab_bwd, t_bwd) if t_bwd >= t_fwd else ("msda_fwd_kernel", ab_fwd, t_fwd)
     achieved = dom[1] / (dom[2] * 1e-3) / 1e9
-    # dram__bytes_read.sum + dram__bytes_write.sum per launch of the same kernels at B=8 fp32, from the ncu --set full
-    # capture committed as profiles/r1_ncu_msda.md (bwd: 1.709 GB + 0.907 GB; fwd: 0.927 GB + 0.313 GB)
-    ncu_traffic = {"msda_bwd_kernel": 2.616e9, "msda_fwd_kernel": 1.240e9} if (dt == 0 and B == 8) else {}
+    # `traffic`: dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of the
+    # SAME kernels at this configuration (profiles/traffic.json names the capture); null when no capture matches
+    traffic, traffic_src = None, None
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        if tj.get("dtype") == args.dtype and tj.get("batch") == B:
+            traffic, traffic_src = tj["kernels"].get(dom[0]), tj.get("capture")
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": dom[0], "achieved": achieved, "peak": peak, "unit": "GB/s",
-                "frac": achieved / peak, "traffic": ncu_traffic.get(dom[0]), "peak_source": peak_src,
-                "limiter": "bwd: L2 atomic units (655 M RED sectors/launch; RED.v4, TMA bulk reduce and tensor TMA reduce all "
-                           "measure 3.03 ms for the scatter alone); fwd: L1 data pipe (pure-gather ceiling 0.85 ms) -- "
-                           "profiles/r1_msda_ceilings.md, DESIGN.md section 4",
+                "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                "limiter": "bwd: issue slots of the tile-sorted segmented reduction (profiles/r2_ncu_msda.md); "
+                           "fwd: L1 data pipe (pure-gather ceiling 0.85 ms, profiles/r1_msda_ceilings.md); DESIGN.md section 4",
                 "algorithmic_bytes_per_launch": dom[1], "launch_ms": dom[2],
                 "fwd": {"ms": t_fwd, "GBps": ab_fwd / (t_fwd * 1e-3) / 1e9},
                 "bwd": {"ms": t_bwd, "GBps": ab_bwd / (t_bwd * 1e-3) / 1e9,
@@ -431,13 +609,43 @@ def main():
         cpu = {"value": Nq / t, "unit": "queries/s", "cores": cores, "kind": "port", "seconds": t,
                "sample": "1 of the step's 8 samples (40000 queries), fwd+bwd, torch CPU grid_sample path, best of 2"}
 
+    if e2e is not None:
+        e2e["aggregate_host_device_GBps"] = world * (h2d + d2h) / (ms_e2e * 1e-3) / 1e9
+
+    # ---- config 5: the end-to-end training step (all ranks; NCCL gradient allreduce + SyncBatchNorm inside the timed region)
+    del pipe, h_out, d_in, out, gv, gl, gw, ws
+    torch.cuda.empty_cache()
+    train = None
+    if not args.no_train:
+        try:
+            train = train_leg(args, dev, rank, world, steps=max(3, min(args.steps, 8)), warmup=3)
+        except Exception as e:                       # never lose the contract line to the secondary legs
+            train = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+    # ---- K3 / K5 alone and config 1 against the REAL reference on the host cores (single-GPU runs only)
+    k3 = k5 = config1 = None
+    if rank == 0 and world == 1 and not args.no_extra:
+        for name, fn in (("k3", k3_leg), ("k5", k5_leg), ("config1", lambda: config1_leg(os.cpu_count() or 1))):
+            try:
+                r = fn()
+            except Exception as e:
+                r = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            if name == "k3":
+                k3 = r
+            elif name == "k5":
+                k5 = r
+            else:
+                config1 = r
+
     if rank == 0:
+        # kernels of libbevr.so launched inside the timed device-resident region: msda_fwd + msda_bwd (sorted) per step,
+        # plus the bf16 cast kernel; the cudaMemsetAsync zero-fill of grad_value is a driver memset, not one of ours
         n_k = 2 if dt == 0 else 3
         line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if dt == 0 else "bf16", "data": "synthetic",
                 "config": workload_config(B, args.dtype), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-                "gpu_launches": args.steps * n_k, "clocks": clk.summary()}
+                "gpu_launches": args.steps * n_k, "train": train, "k3": k3, "k5": k5, "config1": config1,
+                "clocks": clk.summary()}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

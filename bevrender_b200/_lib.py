@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libbevr.so")
+# BEVR_LIB: tuning sweeps load a variant build of the same ABI (scripts/gpu_sweep_*.sh); unset in normal use
+LIB_PATH = os.environ.get("BEVR_LIB") or os.path.join(_HERE, "libbevr.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 _p, _i, _f, _z = C.c_void_p, C.c_int, C.c_float, C.c_size_t
@@ -21,15 +22,13 @@ SIGNATURES = {
     "bevr_msda_fwd": (_i, [_p, _p, _p, _p, _p, _p, _p] + [_i] * 10 + [_p]),
     "bevr_msda_bwd_workspace_bytes": (_z, [_i] * 5),
     "bevr_msda_bwd": (_i, [_p] * 11 + [_i] * 10 + [_p]),
-    "bevr_msda_set_tile": (None, [_i] * 3),
     "bevr_project_points": (_i, [_p] * 6 + [_i] * 3 + [_p]),
     "bevr_affine_warp": (_i, [_p] * 3 + [_i] * 4 + [_p]),
     "bevr_correlate_workspace_bytes": (_z, [_i] * 6),
     "bevr_correlate": (_i, [_p] * 5 + [_i] * 6 + [_p]),
     "bevr_rpe_attn_workspace_bytes": (_z, [_i] * 8),
-    "bevr_rpe_attn_set_mma": (None, [_i]),
-    "bevr_rpe_attn_fwd": (_i, [_p] * 8 + [_i] * 9 + [_f, _p]),
-    "bevr_rpe_attn_bwd": (_i, [_p] * 15 + [_i] * 9 + [_f, _p]),
+    "bevr_rpe_attn_fwd": (_i, [_p] * 8 + [_i] * 9 + [_f, _i, _p]),
+    "bevr_rpe_attn_bwd": (_i, [_p] * 15 + [_i] * 9 + [_f, _i, _p]),
     "bevr_offset_head_fwd": (_i, [_p] * 5 + [C.c_longlong, _p, _p] + [_i] * 7 + [_f, _f, _p]),
     "bevr_offset_head_bwd": (_i, [_p] * 5 + [C.c_longlong] + [_p] * 6 + [_i] * 7 + [_f, _f, _p]),
 }
@@ -46,14 +45,32 @@ def build(force=False):
 
 
 _lib = None
+EXPECTED_VERSION = 200          # BEVR_VERSION of include/bevr.h; bumped with every signature change
+
+
+def _stale():
+    """True if libbevr.so is missing or older than any of its sources (a stale .so with old signatures would be
+    called with the new argtypes: silent memory corruption)."""
+    if os.environ.get("BEVR_LIB"):
+        return False
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    srcs = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh")) or f == "Makefile"]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "bevr.h"))
+    return any(os.path.getmtime(f) > t for f in srcs if os.path.exists(f))
 
 
 def lib():
     global _lib
     if _lib is None:
-        if not os.path.exists(LIB_PATH):
+        if _stale():
             build()
         handle = C.CDLL(LIB_PATH)
+        handle.bevr_version.restype = C.c_int
+        if handle.bevr_version() != EXPECTED_VERSION:
+            raise RuntimeError(f"libbevr.so reports ABI version {handle.bevr_version()}, the host side expects "
+                               f"{EXPECTED_VERSION}: rebuild with make -C bevrender_b200/csrc")
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(handle, name)          # AttributeError if the .so lacks a declared symbol
             fn.restype, fn.argtypes = res, args

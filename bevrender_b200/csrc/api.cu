@@ -22,6 +22,26 @@ int check_launch(const char* what) {
   return (int)e;
 }
 
+int check_cuda(cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return 0;
+  cudaGetLastError();
+  set_error("%s: %s", what, cudaGetErrorString(e));
+  return (int)e;
+}
+
+// The SM count only sizes grids (waves, grid-stride loops); it is a per-device constant, cached per device ordinal.
+int sm_count() {
+  static int cached[64] = {0};
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cached[dev];
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached[dev] = n;                      // benign race: every thread writes the same value
+  }
+  return n;
+}
+
 }  // namespace bevr
 
 extern "C" int bevr_version(void) { return BEVR_VERSION; }

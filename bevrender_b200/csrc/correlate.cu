@@ -294,7 +294,7 @@ static int corr_dims(int C, int Hm, int Wm, int Ht, int Wt, int R, int& NP, int&
   for (int r = CORR_ROWS; r >= 1; --r) {
     if (corr_smem(Wt, NP, r) > 225 * 1024 || (r > 1 && r * NP > 256)) continue;   // merged MMA: N = r * NP <= 256
     const long ctas = (long)xt * ((ho + r - 1) / r);
-    const long cost = ((ctas + 147) / 148) * r;
+    const long cost = ((ctas + sm_count() - 1) / sm_count()) * r;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; rows = r; }
   }
   BEVR_REQUIRE(rows > 0, "correlate: template %d wide x %d rotations does not fit in shared memory", Wt, R);
@@ -326,9 +326,9 @@ extern "C" int bevr_correlate(const float* map, const float* tmpl, const float* 
   __nv_bfloat16* btile = (__nv_bfloat16*)(ws + smap_bytes);
   RotArgs rot;
   for (int r = 0; r < R; ++r) { rot.cs[2 * r] = cosf(angles_rad[r]); rot.cs[2 * r + 1] = sinf(angles_rad[r]); }
-  corr_shift_map_kernel<<<148 * 4, 256, 0, st>>>(map, smap, C, Hm, Wm, Wmp);
+  corr_shift_map_kernel<<<sm_count() * 4, 256, 0, st>>>(map, smap, C, Hm, Wm, Wmp);
   if (int rc = check_launch("correlate shift_map")) return rc;
-  corr_rotate_kernel<<<148 * 4, 256, 0, st>>>(tmpl, rot, btile, C, Ht, Wt, R, NP);
+  corr_rotate_kernel<<<sm_count() * 4, 256, 0, st>>>(tmpl, rot, btile, C, Ht, Wt, R, NP);
   if (int rc = check_launch("correlate rotate")) return rc;
   CorrArgs a;
   a.smap = smap; a.btile = btile; a.out = out;

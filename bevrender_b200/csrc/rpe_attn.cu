@@ -62,19 +62,25 @@ struct Bilin {
 // clamped indices (the bias lookup was 170 of the 237 instructions per (query, key) pair before).
 //
 // Coordinates: grid_sample(align_corners=True) on the displacement (query - key)/2 is, per axis,
-//   i = (((q - p) * 0.5 + 1) * 0.5) * (R - 1)  =  (q * c + c2) - p * c,   c = (R-1)/4, c2 = (R-1)/2  (both exact in fp32)
-// so the query half  A = fma(q, c, c2)  is formed once per query row and the key half  B = p * c  once per key when the
-// tile is staged; a pair costs one subtraction per axis instead of five operations.  Three roundings at magnitude <= R
-// against the reference's three: the coordinate differs from the reference's by ~1 ulp(R) (4e-6 cells at R = 111), far
-// inside the 1e-4 budget because the bilinear lookup is continuous.
-__device__ __forceinline__ float rpe_query_half(float q, int R) { return fmaf(q, 0.25f * (float)(R - 1), 0.5f * (float)(R - 1)); }
-__device__ __forceinline__ float rpe_key_half(float p, int R) { return p * (0.25f * (float)(R - 1)); }
+//   i = (((q - p) * 0.5 + 1) / 2) * (R - 1)
+// and it is evaluated with the REFERENCE's own roundings: fl(q - p); fl(. * 0.5 + 1) (the product is exact, so one FMA);
+// fl(. * (R-1)/2) (the division by two is exact).  The bias itself is continuous in the coordinate, but d bias / d pos is
+// piecewise constant: it jumps where the coordinate crosses a table cell.  Round 1 used the cheaper
+// fma(q, c, c2) - p * c (one subtraction per pair, ~1 ulp(R) away from the reference): at the BASELINE sizes one key in
+// ~300 then had one query column on the other side of such a jump and its grad_pos was off by up to 30 % (5e-2 of
+// max|grad_pos| at N = 50, D = 5; invisible at the N <= 16 golden sizes).  Bit-identical coordinates put every jump
+// where the reference has it.  Cost: 2 extra FP32 instructions per axis per pair.
+__device__ __forceinline__ float rpe_query_half(float q, int) { return q; }
+__device__ __forceinline__ float rpe_key_half(float p, int) { return p; }
+__device__ __forceinline__ float rpe_coord(float q, float p, float half_rm1) {
+  return __fmul_rn(__fmaf_rn(__fsub_rn(q, p), 0.5f, 1.f), half_rm1);
+}
 
 __device__ __forceinline__ Bilin rpe_taps(float ay, float ax, float by, float bx, int Rh, int Rw, int Wp) {
   // clamp to [-2, R]: a clamped sample has ALL four taps in the zero border, so its value and both of its
   // gradients vanish exactly as for an out-of-range grid_sample location (NaN maps to -2 as well)
-  const float ix = fminf(fmaxf(ax - bx, -2.f), (float)Rw);
-  const float iy = fminf(fmaxf(ay - by, -2.f), (float)Rh);
+  const float ix = fminf(fmaxf(rpe_coord(ax, bx, 0.5f * (float)(Rw - 1)), -2.f), (float)Rw);
+  const float iy = fminf(fmaxf(rpe_coord(ay, by, 0.5f * (float)(Rh - 1)), -2.f), (float)Rh);
   Bilin b;
   const float x0f = floorf(ix), y0f = floorf(iy);
   b.wx1 = ix - x0f; b.wx0 = 1.f - b.wx1;
@@ -1186,7 +1192,7 @@ static int grad_copies(int h, int Rh, int Rw) {     // up to 16 private gradient
 // splitting, `per_sm` CTAs resident per SM (register-limited: 4 forward, 3 dQ, 2 dK/dV).  Returns the number of ranges
 // and sets tiles_per_split.  Deterministic in the shapes, so the workspace query and the launch agree.
 static int pick_split(long long base, int per_sm, int n_tiles, int* tiles_per_split) {
-  long long want = (7ll * 148 * per_sm / 2 + base - 1) / base;
+  long long want = (7ll * sm_count() * per_sm / 2 + base - 1) / base;
   if (want > 8) want = 8;
   if (want > n_tiles) want = n_tiles;
   if (want < 1) want = 1;
@@ -1196,17 +1202,15 @@ static int pick_split(long long base, int per_sm, int n_tiles, int* tiles_per_sp
 }
 // Which kernel family serves a call: the mma.sync kernels win from the reference-native shape (56x56) upwards; at very
 // small grids (28x28: 0.6 M (query, key) pairs per head) their fixed costs (operand pre-split launches, fragment loads of
-// 2-tile CTAs) lose to the FFMA2 kernels.  BEVR_K3_MMA=0/1 forces one family (benchmarks, tests).
-static int g_k3_mma = -1;     // -1 auto, 0 FFMA2 kernels, 1 mma.sync kernels (bevr_rpe_attn_set_mma, tuning / test hook)
-static bool use_mma(int Nq, int Ns) {
-  static const int env = [] { const char* e = getenv("BEVR_K3_MMA"); return e ? atoi(e) : -1; }();
-  const int forced = g_k3_mma >= 0 ? g_k3_mma : env;
-  if (forced >= 0) return forced != 0;
+// 2-tile CTAs) lose to the FFMA2 kernels.  The per-call flags BEVR_K3_FFMA / BEVR_K3_MMA force one family (tests, benchmarks).
+static bool use_mma(int Nq, int Ns, int flags) {
+  if (flags & BEVR_K3_MMA) return true;
+  if (flags & BEVR_K3_FFMA) return false;
   return (long long)Nq * Ns >= (3ll << 20);
 }
 
-static int fwd_split(int BH, int Nq, int Ns, int* tps) {
-  if (K3_FWD_MMA && use_mma(Nq, Ns)) return pick_split((long long)((Nq + TQM - 1) / TQM) * BH, K3_MMA_MINB, (Ns + TK - 1) / TK, tps);
+static int fwd_split(int BH, int Nq, int Ns, int flags, int* tps) {
+  if (K3_FWD_MMA && use_mma(Nq, Ns, flags)) return pick_split((long long)((Nq + TQM - 1) / TQM) * BH, K3_MMA_MINB, (Ns + TK - 1) / TK, tps);
   return pick_split((long long)((Nq + TQ - 1) / TQ) * BH, FWD_MINB, (Ns + TK - 1) / TK, tps);
 }
 
@@ -1214,13 +1218,13 @@ static size_t round64(int n) { return ((size_t)n + 63) / 64 * 64; }
 
 // workspace layout (floats): [padded table][backward: gcopies padded gradient tables][forward: key-range partials]
 //                            [K hi, K lo, V hi, V lo : BH * NsP * Dh each][backward: Q hi, Q lo, dO hi, dO lo : BH * NqP * Dh each]
-extern "C" void bevr_rpe_attn_set_mma(int mode) { g_k3_mma = mode; }
-
+// The size covers BOTH kernel families (their forward key splits differ), so it does not depend on the flags of the call.
 extern "C" size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward) {
   size_t n = pad_floats(h, Rh, Rw) * (backward ? 1 + grad_copies(h, Rh, Rw) : 1);
   if (!backward) {
     int tps;
-    const int ks = fwd_split(BH, Nq, Ns, &tps);
+    const int k0 = fwd_split(BH, Nq, Ns, BEVR_K3_FFMA, &tps), k1 = fwd_split(BH, Nq, Ns, BEVR_K3_MMA, &tps);
+    const int ks = k0 > k1 ? k0 : k1;
     if (ks > 1) n += (size_t)ks * BH * (Dh + 2) * Nq;
   }
   n += 4 * (size_t)BH * round64(Ns) * Dh;
@@ -1248,7 +1252,7 @@ static float* presplit_kv(RpeArgs& a, const float* k, const float* v, float* bas
 
 extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
                                  float* out, float* lse, void* workspace, int BH, int h, int hpg, int Dh, int Hq,
-                                 int Wq, int Ns, int Rh, int Rw, float scale, void* stream) {
+                                 int Wq, int Ns, int Rh, int Rw, float scale, int flags, void* stream) {
   if (int rc = validate(BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw)) return rc;
   BEVR_REQUIRE(q && k && v && rpe && pos && out && lse && workspace, "rpe_attn_fwd: NULL pointer argument");
   RpeArgs a = {};
@@ -1256,13 +1260,13 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
   a.Hp = Rh + 4; a.Wp = Rw + 4;
   a.scale = scale;
-  a.split = fwd_split(BH, a.Nq, Ns, &a.tiles_per_split);
+  a.split = fwd_split(BH, a.Nq, Ns, flags, &a.tiles_per_split);
   a.part_o = (float*)workspace + pad_floats(h, Rh, Rw);
   a.part_ml = a.part_o + (size_t)a.split * BH * Dh * a.Nq;
   cudaStream_t st = (cudaStream_t)stream;
-  rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, (float*)workspace, h, Rh, Rw);
+  rpe_pad_kernel<<<sm_count(), 256, 0, st>>>(rpe, (float*)workspace, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_fwd pad")) return rc;
-  const bool mma = K3_FWD_MMA && use_mma(a.Nq, Ns);
+  const bool mma = K3_FWD_MMA && use_mma(a.Nq, Ns, flags);
   if (mma) {
     int rc = 0;
     presplit_kv(a, k, v, a.part_o + (a.split > 1 ? (size_t)a.split * BH * (Dh + 2) * a.Nq : 0), Dh, st, &rc);
@@ -1291,7 +1295,7 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
                                  const float* out, const float* lse, const float* grad_out, float* grad_q,
                                  float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos, float* delta_ws,
                                  void* workspace, int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns, int Rh,
-                                 int Rw, float scale, void* stream) {
+                                 int Rw, float scale, int flags, void* stream) {
   if (int rc = validate(BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw)) return rc;
   BEVR_REQUIRE(q && k && v && rpe && pos && out && lse && grad_out && delta_ws && workspace,
                "rpe_attn_bwd: NULL pointer argument");
@@ -1307,10 +1311,11 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   a.Hp = Rh + 4; a.Wp = Rw + 4;
   a.scale = scale;
   cudaStream_t st = (cudaStream_t)stream;
-  rpe_pad_kernel<<<148, 256, 0, st>>>(rpe, pad, h, Rh, Rw);
+  rpe_pad_kernel<<<sm_count(), 256, 0, st>>>(rpe, pad, h, Rh, Rw);
   if (int rc = check_launch("rpe_attn_bwd pad")) return rc;
-  if (grad_rpe) cudaMemsetAsync(gpad, 0, pad_floats(h, Rh, Rw) * sizeof(float) * a.gcopies, st);
-  const bool mma_dq = K3_DQ_MMA && use_mma(a.Nq, Ns), mma_dkv = K3_DKV_MMA && use_mma(a.Nq, Ns);
+  if (grad_rpe)
+    if (int rc = check_cuda(cudaMemsetAsync(gpad, 0, pad_floats(h, Rh, Rw) * sizeof(float) * a.gcopies, st), "rpe_attn_bwd zero-fill")) return rc;
+  const bool mma_dq = K3_DQ_MMA && use_mma(a.Nq, Ns, flags), mma_dkv = K3_DKV_MMA && use_mma(a.Nq, Ns, flags);
   if (mma_dq || mma_dkv) {
     int rc = 0;
     float* nxt = presplit_kv(a, k, v, gpad + pad_floats(h, Rh, Rw) * a.gcopies, Dh, st, &rc);
@@ -1332,7 +1337,8 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
     const int tq = mma_dq ? TQM : TQ;
     const int nqt = (a.Nq + tq - 1) / tq;
     a.split = pick_split((long long)nqt * BH, mma_dq ? K3_DQ_MMA_MINB : K3_DQ_MINB, (Ns + TK - 1) / TK, &a.tiles_per_split);
-    if (a.split > 1) cudaMemsetAsync(grad_q, 0, (size_t)BH * Dh * a.Nq * sizeof(float), st);
+    if (a.split > 1)
+      if (int rc = check_cuda(cudaMemsetAsync(grad_q, 0, (size_t)BH * Dh * a.Nq * sizeof(float), st), "rpe_attn_bwd zero-fill")) return rc;
     if (mma_dq) {
       if (Dh == 32) rpe_attn_bwd_dq_mma_kernel<32><<<dim3(nqt, BH, a.split), 128, 0, st>>>(a);
       else rpe_attn_bwd_dq_mma_kernel<16><<<dim3(nqt, BH, a.split), 128, 0, st>>>(a);
@@ -1348,8 +1354,10 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
     const int per_sm = mma_dkv ? K3_DKV_MMA_MINB : (DKV_MINB < 2 ? 2 : DKV_MINB);
     a.split = pick_split((long long)nkt * BH, per_sm, nqt, &a.tiles_per_split);
     if (a.split > 1) {
-      if (grad_k) cudaMemsetAsync(grad_k, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
-      if (grad_v) cudaMemsetAsync(grad_v, 0, (size_t)BH * Dh * Ns * sizeof(float), st);
+      if (grad_k)
+        if (int rc = check_cuda(cudaMemsetAsync(grad_k, 0, (size_t)BH * Dh * Ns * sizeof(float), st), "rpe_attn_bwd zero-fill")) return rc;
+      if (grad_v)
+        if (int rc = check_cuda(cudaMemsetAsync(grad_v, 0, (size_t)BH * Dh * Ns * sizeof(float), st), "rpe_attn_bwd zero-fill")) return rc;
     }
     if (mma_dkv) {
       if (Dh == 32) rpe_attn_bwd_dkv_mma_kernel<32><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a);
@@ -1361,7 +1369,7 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
     if (int rc = check_launch("rpe_attn_bwd dkv")) return rc;
   }
   if (grad_rpe) {
-    rpe_unpad_add_kernel<<<148, 256, 0, st>>>(gpad, grad_rpe, h, Rh, Rw, a.gcopies);
+    rpe_unpad_add_kernel<<<sm_count(), 256, 0, st>>>(gpad, grad_rpe, h, Rh, Rw, a.gcopies);
     if (int rc = check_launch("rpe_attn_bwd unpad")) return rc;
   }
   return 0;

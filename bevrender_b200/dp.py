@@ -16,19 +16,41 @@ parameter bitmap allreduce and per-iteration buffer broadcast, the B200 design i
 
 One process per GPU; NCCL over NVLink for CUDA tensors, gloo for the CPU tests.
 """
-import re
-
 import torch
 import torch.distributed as dist
 
-DEAD_PARAM_PATTERNS = (r"(^|\.)proj_q\.", r"(^|\.)proj_views\.", r"(^|\.)conv_offset_m[12]\.")
+# sub-modules of TSADeformableAttention / SCADeformableAttention that exist only for state_dict compatibility
+# (SURVEY.md appendix B): never applied in forward, so their parameters never receive a gradient
+DEAD_SUBMODULES = ("proj_q", "proj_views", "conv_offset_m1", "conv_offset_m2")
 
 
 def live_named_parameters(module):
-    """Trainable parameters minus the ones the reference (and the drop-in modules) never use."""
-    dead = [re.compile(p) for p in DEAD_PARAM_PATTERNS]
-    return [(n, p) for n, p in module.named_parameters()
-            if p.requires_grad and not any(d.search(n) for d in dead)]
+    """Trainable parameters minus the ones the deformable-attention modules never use.  Only parameters OWNED by a
+    TSADeformableAttention / SCADeformableAttention instance (this package's or the reference's) are filtered: a
+    caller's own ``proj_q`` elsewhere in the model stays live."""
+    dead = set()
+    for m in module.modules():
+        if type(m).__name__ in ("TSADeformableAttention", "SCADeformableAttention"):
+            for name in DEAD_SUBMODULES:
+                sub = getattr(m, name, None)
+                if isinstance(sub, torch.nn.Module):
+                    dead.update(id(p) for p in sub.parameters())
+    return [(n, p) for n, p in module.named_parameters() if p.requires_grad and id(p) not in dead]
+
+
+def find_live_parameters(module, run_step):
+    """Static replacement for DDP's ``find_unused_parameters=True`` (train.py:134): run ONE forward + backward
+    (``run_step()`` must call ``.backward()``) and return the (name, parameter) pairs that received a gradient.  The
+    reference model carries parameters no forward ever touches (FeedForwardLayer is built but not called,
+    encoder.py:291-296,383,404; the dead projections above): DDP re-discovers them with a bitmap allreduce every
+    iteration, here they are excluded once, before the flat bucket is laid out."""
+    for p in module.parameters():
+        p.grad = None
+    run_step()
+    live = [(n, p) for n, p in module.named_parameters() if p.requires_grad and p.grad is not None]
+    for p in module.parameters():
+        p.grad = None
+    return live
 
 
 class FlatGradAllReduce:
@@ -37,6 +59,10 @@ class FlatGradAllReduce:
         self.group = group
         self.average = average
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if self.world > 1:                     # as DDP does at construction: every rank starts from rank 0's weights
+            with torch.no_grad():
+                for p in self.params:
+                    dist.broadcast(p.data, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
         dev, total = self.params[0].device, sum(p.numel() for p in self.params)
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
         # lay parameters out in REVERSE registration order: the last layers' grads are ready first and

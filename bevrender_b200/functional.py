@@ -11,7 +11,7 @@ import torch
 from . import _lib
 
 F32, BF16 = 0, 1
-ALIGN_CORNERS, LOC_PM1, OFFSET_PIXELS, ACCUMULATE = 1, 2, 4, 8
+ALIGN_CORNERS, LOC_PM1, OFFSET_PIXELS, ACCUMULATE, BWD_DIRECT = 1, 2, 4, 8, 16
 _DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
 
 
@@ -90,16 +90,17 @@ class _MSDA(torch.autograd.Function):
 
 def ms_deform_attn(value, spatial_shapes, level_start_index, sampling_locations, attention_weights=None,
                    reference_points=None, query_w=0, align_corners=False, loc_pm1=False,
-                   offset_in_pixels=False):
+                   offset_in_pixels=False, bwd_direct=False):
     """Multi-scale deformable attention gather (kernels K1/K2).
 
     value (B,S,h,Dh) fp32|bf16 channels-last; sampling_locations (B,Nq,h,L,P,2) fp32 (x,y) --
     or sampling OFFSETS when ``reference_points`` (B,Nq,L,2) is given (loc = ref + off, with
     off / (W_l,H_l) if ``offset_in_pixels``); attention_weights (B,Nq,h,L,P) or None (== 1).
     Returns (B, Nq, h*Dh).  ``query_w``: width of the 2-D query grid (enables 2-D tiling).
+    ``bwd_direct``: backward with one RED per tap instead of the tile-sorted kernel (BEVR_BWD_DIRECT).
     """
     flags = (ALIGN_CORNERS if align_corners else 0) | (LOC_PM1 if loc_pm1 else 0) | \
-            (OFFSET_PIXELS if offset_in_pixels else 0)
+            (OFFSET_PIXELS if offset_in_pixels else 0) | (BWD_DIRECT if bwd_direct else 0)
     shapes = _as_tuple(spatial_shapes, pair=True)
     starts = _as_tuple(level_start_index)
     return _MSDA.apply(value, sampling_locations, attention_weights, reference_points, shapes, starts,
@@ -139,7 +140,7 @@ def project_points(points, cam_T, K, img_w, img_h):
 
 class _RpeAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, rpe, pos, Hq, Wq, hpg, scale):
+    def forward(ctx, q, k, v, rpe, pos, Hq, Wq, hpg, scale, flags):
         _need_cuda(q, k, v, rpe, pos)
         q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
         rpe, pos = rpe.contiguous().float(), pos.contiguous().float()
@@ -150,16 +151,16 @@ class _RpeAttention(torch.autograd.Function):
         lse = torch.empty(BH, Nq, dtype=torch.float32, device=q.device)
         ws = torch.empty(_lib.lib().bevr_rpe_attn_workspace_bytes(BH, h, Dh, Nq, Ns, Rh, Rw, 0), dtype=torch.uint8, device=q.device)
         _lib.check(_lib.lib().bevr_rpe_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
-                                                _ptr(ws), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, float(scale), _stream()),
+                                                _ptr(ws), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, float(scale), flags, _stream()),
                    "bevr_rpe_attn_fwd")
         ctx.save_for_backward(q, k, v, rpe, pos, out, lse)
-        ctx.meta = (Hq, Wq, hpg, float(scale))
+        ctx.meta = (Hq, Wq, hpg, float(scale), flags)
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         q, k, v, rpe, pos, out, lse = ctx.saved_tensors
-        Hq, Wq, hpg, scale = ctx.meta
+        Hq, Wq, hpg, scale, flags = ctx.meta
         BH, Dh, Nq = q.shape
         Ns = k.shape[2]
         h, Rh, Rw = rpe.shape
@@ -175,21 +176,25 @@ class _RpeAttention(torch.autograd.Function):
         _lib.check(_lib.lib().bevr_rpe_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
                                                 _ptr(grad_out), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(gr), _ptr(gp),
                                                 _ptr(delta), _ptr(ws), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, scale,
-                                                _stream()),
+                                                flags, _stream()),
                    "bevr_rpe_attn_bwd")
-        return gq, gk, gv, gr, gp, None, None, None, None
+        return gq, gk, gv, gr, gp, None, None, None, None, None
 
 
-def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None):
+K3_AUTO, K3_FFMA, K3_MMA = 0, 1, 2
+
+
+def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None, family=K3_AUTO):
     """K3: softmax_j(q.k*scale + bilinear(rpe_table[head], (qgrid_i - pos_j)/2)) . v, never materialised.
 
     q (B*h, Dh, Hq*Wq); k, v (B*h, Dh, Ns); rpe_table (h, Rh, Rw); pos (B*g, Ns, 2) in (y, x);
     returns (B*h, Dh, Hq*Wq).  Replaces TSA_deform_attn.py:245-330 / SCA_deform_attn.py:331-411.
+    ``family``: K3_AUTO picks the kernel family by problem size; K3_FFMA / K3_MMA force one (tests, benchmarks).
     """
     h = rpe_table.shape[0]
     if scale is None:
         scale = q.shape[1] ** -0.5
-    return _RpeAttention.apply(q, k, v, rpe_table, pos, int(Hq), int(Wq), h // n_groups, scale)
+    return _RpeAttention.apply(q, k, v, rpe_table, pos, int(Hq), int(Wq), h // n_groups, scale, int(family))
 
 
 class _OffsetHead(torch.autograd.Function):

