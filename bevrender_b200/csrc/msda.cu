@@ -879,15 +879,19 @@ static bool sorted_applicable(int Dh, int L, int P) {
   return Dh % 4 == 0 && Dh <= 128 && pick_lpg_pow2(Dh / 4) && tq >= 8 && tq * L * P <= 8192;
 }
 
+#ifndef MSDA_SORT_GO_BYTES
+#define MSDA_SORT_GO_BYTES (16 * 1024)   // stage the tile's grad_out rows in shared memory up to this size
+#endif
 #ifndef MSDA_SORT_NV
-#define MSDA_SORT_NV 8             // channels per lane of the sorted backward when Dh allows it (else 4)
+#define MSDA_SORT_NV 4             // channels per lane of the sorted backward (8 halves the per-point overhead but needs 118 registers:
+                                   // 3.47 ms against 3.01 ms at BASELINE config 2, profiles/r2_sweep_msda_sorted.txt)
 #endif
 
 template <typename T, int NV, int LPG>
 static int launch_sorted(MsdaArgs& a, cudaStream_t st) {
   const int LP = a.L * a.P, tq = a.th << a.tw_shift, NP = tq * LP, row4 = a.Dh / 4;
   const int maxbins = MSDA_SORT_MAXBINS;
-  a.sort_go_smem = (size_t)tq * row4 * 16 <= 16 * 1024;
+  a.sort_go_smem = (size_t)tq * row4 * 16 <= MSDA_SORT_GO_BYTES;
   size_t bytes = (size_t)NP * 40 + (a.sort_go_smem ? (size_t)tq * row4 * 16 : 0) + (size_t)(maxbins + 1) * 4 + (size_t)NP * 2;
   bytes = (bytes + 15) & ~(size_t)15;
   a.sort_lvl_off = (int)bytes;
