@@ -39,10 +39,6 @@ struct RpeArgs {
   const float *kh, *kl, *vh, *vl, *qh, *ql, *gh, *gl;
   int NsP, NqP;
   float scale;
-  // "regular" axes (Rh == 2 Hq - 1, Rw == 2 Wq - 1): the table coordinate of (query index i, key position p) is
-  // i + c(p): its floor and fraction are per-key constants (rpe_key_regular); delta = margin around the cell boundaries
-  int yreg, xreg;
-  float dly, dlx;
 };
 
 // DH (channels per head) is a template parameter of every kernel: 32 (the reference, encoder.py:23-39) and 16.
@@ -93,58 +89,6 @@ __device__ __forceinline__ Bilin rpe_taps(float ay, float ax, float by, float bx
   return b;
 }
 
-// ---- per-key constants of a regular axis (the mma kernels' fast path)
-// With R = 2n - 1 and q_i = 2i/(n-1) - 1 the coordinate above is, in exact arithmetic, i + c,  c = (n-1)(1-p)/2: it
-// advances by exactly one cell per query row / column.  floor and fraction are then PER-KEY constants, and a pair costs
-// an integer add instead of sub / fma / mul / 2 clamps / floor / sub / cvt per axis (65 % of the kernels' instructions
-// were this set-up).  The reference's fp32 chain and c differ by < 2.3e-7 R cells, so wherever the fraction of c is at
-// least `delta` = 4e-7 R + 2e-5 away from both cell boundaries every query's floor agrees with the reference's (the jumps
-// of d bias / d pos stay where the reference has them) and the bilinear weights agree to 1e-4 cells; the < 0.1 % of keys
-// inside the margin (or outside the table by more than a cell) send their 8-key tile / 16-key warp down the exact path.
-struct KeyReg { float f; int i0; bool ok; };
-__device__ __forceinline__ KeyReg rpe_key_regular(float p, int n, float delta) {
-  const float c = (0.5f * (float)(n - 1)) * (1.f - p);
-  const float c0 = floorf(c);
-  KeyReg k;
-  k.f = c - c0;
-  k.ok = (c >= -1.5f) && (c <= (float)n - 0.5f) && (k.f >= delta) && (k.f <= 1.f - delta);   // false for NaN
-  k.i0 = k.ok ? (int)c0 : 0;
-  return k;
-}
-// key record of the fast path: x = fraction along y, y = fraction along x (XREG) or raw position x, z = table offset bits
-template <bool XREG>
-__device__ __forceinline__ Bilin rpe_taps_fast(int qoff, float ax, const float4& k, int Rw) {
-  Bilin b;
-  b.wy1 = k.x; b.wy0 = 1.f - k.x;
-  if (XREG) {
-    b.wx1 = k.y; b.wx0 = 1.f - k.y;
-    b.off = qoff + __float_as_int(k.z);
-  } else {
-    const float ix = fminf(fmaxf(rpe_coord(ax, k.y, 0.5f * (float)(Rw - 1)), -2.f), (float)Rw);
-    const float x0f = floorf(ix);
-    b.wx1 = ix - x0f; b.wx0 = 1.f - b.wx1;
-    b.off = qoff + __float_as_int(k.z) + (int)x0f;
-  }
-  return b;
-}
-// stage TK key positions for the query-row kernels: per key a float4 record, per 8 keys (one n-tile of the mma
-// kernels: warp-uniform) a flag whether all of them take the fast path.  Called by all threads of a 128-thread CTA.
-__device__ __forceinline__ void rpe_stage_keys(float4* sKey, unsigned char* sFast, const float2* pb, int j0, int n_keys,
-                                               const RpeArgs& a) {
-  for (int jj = threadIdx.x; jj < n_keys; jj += blockDim.x) {        // n_keys is a multiple of 32: whole warps
-    const bool in = j0 + jj < a.Ns;
-    const float2 p = in ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
-    const KeyReg ky = rpe_key_regular(p.x, a.Hq, a.dly), kx = rpe_key_regular(p.y, a.Wq, a.dlx);
-    const bool ok = !in || (a.yreg && ky.ok && (!a.xreg || kx.ok));
-    const unsigned vote = __ballot_sync(0xffffffffu, ok);
-    const int lane = threadIdx.x & 31;
-    const bool fast = a.yreg && ((vote >> (lane & 24)) & 0xffu) == 0xffu;
-    float4 rec = make_float4(p.x, p.y, 0.f, 0.f);
-    if (fast) rec = make_float4(ky.f, a.xreg ? kx.f : p.y, __int_as_float(ky.i0 * a.Wp + (a.xreg ? kx.i0 : 0)), 0.f);
-    sKey[jj] = rec;
-    if ((lane & 7) == 0) sFast[jj >> 3] = fast ? 1 : 0;
-  }
-}
 // bias value; tapv receives the four tap values (zero where the tap is outside the table)
 __device__ __forceinline__ float rpe_bias(const float* tbl, const Bilin& b, int Wp, float* tapv) {
   const float* r0 = tbl + b.off;
@@ -466,8 +410,7 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
   constexpr int KS = DH / 8;                 // k-steps of S = Q^T K (channels) = n-tiles of O (channels)
   constexpr int NT = CHM / 8;                // key n-tiles per softmax step = k-steps of O += P V
   __shared__ __align__(16) float sKh[TK * PAD], sKl[TK * PAD], sVh[TK * PAD], sVl[TK * PAD];
-  __shared__ __align__(16) float4 sKey[TK];
-  __shared__ unsigned char sFast[TK / 8];
+  __shared__ __align__(16) float2 sPos[TK];
   const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
@@ -478,14 +421,12 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
   const int i0 = blockIdx.x * TQM + warp * 16;
   int iq[2] = {i0 + g, i0 + g + 8};
   float ay[2], ax[2], m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
-  int qoff[2];                               // fast path: table offset of the query's own row / column
   uint32_t qh[KS][4], ql[KS][4];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int iy = iq[r] / a.Wq, ixq = iq[r] - iy * a.Wq;
     ay[r] = rpe_query_half(grid_coord(iy, a.Hq), a.Rh);
     ax[r] = rpe_query_half(grid_coord(ixq, a.Wq), a.Rw);
-    qoff[r] = iy * a.Wp + (a.xreg ? ixq : 0);
   }
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks)
@@ -510,7 +451,10 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
       stage_async<DH>(sKh, a.kh + tile); stage_async<DH>(sKl, a.kl + tile);
       stage_async<DH>(sVh, a.vh + tile); stage_async<DH>(sVl, a.vl + tile);
     }
-    rpe_stage_keys(sKey, sFast, pb, j0, TK, a);
+    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x) {
+      const float2 p = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+      sPos[jj] = make_float2(rpe_key_half(p.x, a.Rh), rpe_key_half(p.y, a.Rw));
+    }
     stage_async_wait();
     __syncthreads();
 #pragma unroll 1
@@ -541,15 +485,11 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
       float mx[2] = {-INFINITY, -INFINITY};
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const float4 k0 = sKey[jc + nt * 8 + 2 * t], k1 = sKey[jc + nt * 8 + 2 * t + 1];   // this lane's two keys
-        const int fast = sFast[(jc >> 3) + nt] ? (a.xreg ? 2 : 1) : 0;                      // warp-uniform
+        const float4 pp = *reinterpret_cast<const float4*>(&sPos[jc + nt * 8 + 2 * t]);   // two keys' halves
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int r = e >> 1, kk = e & 1;
-          const float4 kq = kk ? k1 : k0;
-          const Bilin b = fast == 2 ? rpe_taps_fast<true>(qoff[r], ax[r], kq, a.Rw)
-                        : fast == 1 ? rpe_taps_fast<false>(qoff[r], ax[r], kq, a.Rw)
-                                    : rpe_taps(ay[r], ax[r], kq.x, kq.y, a.Rh, a.Rw, a.Wp);
+          const Bilin b = rpe_taps(ay[r], ax[r], kk ? pp.z : pp.x, kk ? pp.w : pp.y, a.Rh, a.Rw, a.Wp);
           float tv[4];
           const float v = sc[nt][e] + rpe_bias(table, b, a.Wp, tv);
           sc[nt][e] = (j0 + jc + nt * 8 + 2 * t + kk < a.Ns) ? v : -INFINITY;
@@ -745,8 +685,7 @@ template <int DH>
 __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kernel(const __grid_constant__ RpeArgs a) {
   constexpr int KS = DH / 8, NT = CHM / 8;
   __shared__ __align__(16) float sKh[TK * PAD], sKl[TK * PAD], sVh[TK * PAD], sVl[TK * PAD];
-  __shared__ __align__(16) float4 sKey[TK];
-  __shared__ unsigned char sFast[TK / 8];
+  __shared__ __align__(16) float2 sPos[TK];
   const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
@@ -757,14 +696,12 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
   const int i0 = blockIdx.x * TQM + warp * 16;
   const int iq[2] = {i0 + g, i0 + g + 8};
   float ay[2], ax[2], lse[2], delta[2];
-  int qoff[2];
   uint32_t qh[KS][4], ql[KS][4], gh[KS][4], gl[KS][4];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int iy = iq[r] / a.Wq, ixq = iq[r] - iy * a.Wq;
     ay[r] = rpe_query_half(grid_coord(iy, a.Hq), a.Rh);
     ax[r] = rpe_query_half(grid_coord(ixq, a.Wq), a.Rw);
-    qoff[r] = iy * a.Wp + (a.xreg ? ixq : 0);
     const bool live = iq[r] < a.Nq;
     lse[r] = live ? __ldg(a.lse + (size_t)bh * a.Nq + iq[r]) : 0.f;
     delta[r] = live ? __ldg(a.delta + (size_t)bh * a.Nq + iq[r]) : 0.f;
@@ -794,7 +731,10 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
       stage_async<DH>(sKh, a.kh + tile); stage_async<DH>(sKl, a.kl + tile);
       stage_async<DH>(sVh, a.vh + tile); stage_async<DH>(sVl, a.vl + tile);
     }
-    rpe_stage_keys(sKey, sFast, pb, j0, TK, a);
+    for (int jj = threadIdx.x; jj < TK; jj += blockDim.x) {
+      const float2 p = (j0 + jj < a.Ns) ? __ldg(pb + j0 + jj) : make_float2(0.f, 0.f);
+      sPos[jj] = make_float2(rpe_key_half(p.x, a.Rh), rpe_key_half(p.y, a.Rw));
+    }
     stage_async_wait();
     __syncthreads();
 #pragma unroll 1
@@ -836,15 +776,11 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
       // dS = P (dP - delta), P = exp(S + bias - lse); element e of tile nt: row (e >> 1), key jc + nt*8 + 2t + (e & 1)
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
-        const float4 k0 = sKey[jc + nt * 8 + 2 * t], k1 = sKey[jc + nt * 8 + 2 * t + 1];
-        const int fast = sFast[(jc >> 3) + nt] ? (a.xreg ? 2 : 1) : 0;
+        const float4 pp = *reinterpret_cast<const float4*>(&sPos[jc + nt * 8 + 2 * t]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int r = e >> 1, kk = e & 1;
-          const float4 kq = kk ? k1 : k0;
-          const Bilin b = fast == 2 ? rpe_taps_fast<true>(qoff[r], ax[r], kq, a.Rw)
-                        : fast == 1 ? rpe_taps_fast<false>(qoff[r], ax[r], kq, a.Rw)
-                                    : rpe_taps(ay[r], ax[r], kq.x, kq.y, a.Rh, a.Rw, a.Wp);
+          const Bilin b = rpe_taps(ay[r], ax[r], kk ? pp.z : pp.x, kk ? pp.w : pp.y, a.Rh, a.Rw, a.Wp);
           float tv[4];
           const float pr = __expf(sc[nt][e] + rpe_bias(table, b, a.Wp, tv) - lse[r]);
           sc[nt][e] = (j0 + jc + nt * 8 + 2 * t + kk < a.Ns) ? pr * (dp[nt][e] - delta[r]) : 0.f;
@@ -1034,7 +970,6 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
   constexpr int KS = DH / 8, NT = CHM / 8;
   __shared__ __align__(16) float sQh[TK * PAD], sQl[TK * PAD], sGh[TK * PAD], sGl[TK * PAD];
   __shared__ __align__(16) float4 sRow[TK];  // query halves of the bias coordinates (y, x), lse, delta
-  __shared__ __align__(8) int sQoff[TK];     // fast path: table offset of the query's own row / column
   const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
@@ -1047,20 +982,13 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
   const int j0w = blockIdx.x * TKM + warp * 16;
   const int jk[2] = {j0w + g, j0w + g + 8};
   float by[2], bx[2], giy[2] = {0.f, 0.f}, gix[2] = {0.f, 0.f};
-  float4 kfast[2];                           // fast path: this lane's two keys as rpe_taps_fast records
-  bool keys_ok = true;
   uint32_t kh[KS][4], kl[KS][4], vh[KS][4], vl[KS][4];
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     float2 p = make_float2(0.f, 0.f);
     if (jk[r] < a.Ns) p = __ldg(reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns + jk[r]);
     by[r] = rpe_key_half(p.x, a.Rh); bx[r] = rpe_key_half(p.y, a.Rw);
-    const KeyReg ky = rpe_key_regular(p.x, a.Hq, a.dly), kx = rpe_key_regular(p.y, a.Wq, a.dlx);
-    keys_ok = keys_ok && (jk[r] >= a.Ns || (ky.ok && (!a.xreg || kx.ok)));
-    kfast[r] = make_float4(ky.f, a.xreg ? kx.f : p.y, __int_as_float(ky.i0 * a.Wp + (a.xreg ? kx.i0 : 0)), 0.f);
   }
-  // the keys of a warp never change: one decision per warp for the whole kernel
-  const int fast = (a.yreg && __all_sync(0xffffffffu, keys_ok)) ? (a.xreg ? 2 : 1) : 0;
 #pragma unroll
   for (int ks = 0; ks < KS; ++ks)
 #pragma unroll
@@ -1093,9 +1021,6 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
         const int iy = i / a.Wq, ixq = i - iy * a.Wq;
         r = make_float4(rpe_query_half(grid_coord(iy, a.Hq), a.Rh), rpe_query_half(grid_coord(ixq, a.Wq), a.Rw),
                         __ldg(a.lse + (size_t)bh * a.Nq + i), __ldg(a.delta + (size_t)bh * a.Nq + i));
-        sQoff[ii] = iy * a.Wp + (a.xreg ? ixq : 0);
-      } else {
-        sQoff[ii] = 0;
       }
       sRow[ii] = r;
     }
@@ -1141,14 +1066,11 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
 #pragma unroll
       for (int nt = 0; nt < NT; ++nt) {
         const float4 r0 = sRow[jc + nt * 8 + 2 * t], r1 = sRow[jc + nt * 8 + 2 * t + 1];
-        const int2 qo = *reinterpret_cast<const int2*>(&sQoff[jc + nt * 8 + 2 * t]);
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const int r = e >> 1, kk = e & 1;
           const float4 rq = kk ? r1 : r0;
-          const Bilin b = fast == 2 ? rpe_taps_fast<true>(kk ? qo.y : qo.x, rq.y, kfast[r], a.Rw)
-                        : fast == 1 ? rpe_taps_fast<false>(kk ? qo.y : qo.x, rq.y, kfast[r], a.Rw)
-                                    : rpe_taps(rq.x, rq.y, by[r], bx[r], a.Rh, a.Rw, a.Wp);
+          const Bilin b = rpe_taps(rq.x, rq.y, by[r], bx[r], a.Rh, a.Rw, a.Wp);
           float tv[4];
           const bool ok = (i0 + jc + nt * 8 + 2 * t + kk < a.Nq) && (jk[r] < a.Ns);
           const float bias = rpe_bias(table, b, a.Wp, tv);          // always sampled: the taps feed the gradients below
@@ -1337,8 +1259,6 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   a.q = q; a.k = k; a.v = v; a.rpe_pad = (const float*)workspace; a.pos = pos; a.o_out = out; a.o_lse = lse;
   a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
   a.Hp = Rh + 4; a.Wp = Rw + 4;
-  a.yreg = (Rh == 2 * Hq - 1); a.xreg = (Rw == 2 * Wq - 1);
-  a.dly = 4e-7f * (float)Rh + 2e-5f; a.dlx = 4e-7f * (float)Rw + 2e-5f;
   a.scale = scale;
   a.split = fwd_split(BH, a.Nq, Ns, flags, &a.tiles_per_split);
   a.part_o = (float*)workspace + pad_floats(h, Rh, Rw);
@@ -1389,8 +1309,6 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
   a.grad_pos = grad_pos;
   a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
   a.Hp = Rh + 4; a.Wp = Rw + 4;
-  a.yreg = (Rh == 2 * Hq - 1); a.xreg = (Rw == 2 * Wq - 1);
-  a.dly = 4e-7f * (float)Rh + 2e-5f; a.dlx = 4e-7f * (float)Rw + 2e-5f;
   a.scale = scale;
   cudaStream_t st = (cudaStream_t)stream;
   rpe_pad_kernel<<<sm_count(), 256, 0, st>>>(rpe, pad, h, Rh, Rw);
