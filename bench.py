@@ -447,6 +447,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true", help="tuning sweeps only: skip the host-buffer leg")
+    ap.add_argument("--bf16-out-grad", dest="bf16_grad_f32", action="store_false",
+                    help="--dtype bf16: deliver grad_value in bf16 (fp32 workspace + cast) instead of fp32 main gradients")
     ap.add_argument("--no-train", action="store_true", help="skip the config-5 training-step leg")
     ap.add_argument("--no-extra", action="store_true", help="skip the K3 / K5 / config-1 legs")
     ap.add_argument("--workload", default="msda", choices=["msda", "train"],
@@ -488,7 +490,10 @@ def main():
     h_in = {k: host[k].contiguous().pin_memory() for k in names}
     d_in = {k: h_in[k].to(dev) for k in names}
     out = torch.empty(B, Nq, HEADS * DH, dtype=tdt, device=dev)
-    gv = torch.empty(B, S, HEADS, DH, dtype=tdt, device=dev)
+    # bf16 storage keeps fp32 main gradients for value (BEVR_GRAD_VALUE_F32): "grad_value accumulated fp32" of BASELINE.json
+    # config 2 without the workspace + cast pass the bf16-output path needs
+    gv = torch.empty(B, S, HEADS, DH, dtype=torch.float32 if args.bf16_grad_f32 else tdt, device=dev)
+    bwd_flags = 32 if (dt == 1 and args.bf16_grad_f32) else 0
     gl = torch.empty(B, Nq, HEADS, LEVELS, POINTS, 2, dtype=torch.float32, device=dev)
     gw = torch.empty(B, Nq, HEADS, LEVELS, POINTS, dtype=tdt, device=dev)
     nws = L.bevr_msda_bwd_workspace_bytes(B, S, HEADS, DH, dt)
@@ -504,7 +509,7 @@ def main():
     def bwd(dd, stream):
         _lib.check(L.bevr_msda_bwd(P(dd["value"]), hw, st, P(dd["sampling_locations"]), None, P(dd["attention_weights"]),
                                    P(dd["grad_out"]), P(gv), P(gl), P(gw), P(ws), B, S, HEADS, DH, Nq, LEVELS, POINTS,
-                                   N_SIDE, dt, 0, stream), "msda_bwd")
+                                   N_SIDE, dt, bwd_flags, stream), "msda_bwd")
 
     cur = torch.cuda.current_stream()
     cs = C.c_void_p(cur.cuda_stream)
@@ -576,7 +581,7 @@ def main():
     # ---- end-to-end leg: HOST pinned inputs -> H2D -> fwd+bwd -> D2H of every result, per step, through the
     # host-buffer entry point (per-sample chunks pipelined over H2D / compute / D2H streams)
     from bevrender_b200.host_pipeline import HostMsdaPipeline
-    h_out = {k: torch.empty(t.shape, dtype=t.dtype).pin_memory() for k, t in
+    h_out = {k: torch.empty(t.shape, dtype=(tdt if k == "grad_value" else t.dtype)).pin_memory() for k, t in
              (("out", out), ("grad_value", gv), ("grad_loc", gl), ("grad_weight", gw))}
     h2d = sum(t.numel() * t.element_size() for t in h_in.values())
     d2h = sum(t.numel() * t.element_size() for t in h_out.values())
@@ -639,11 +644,12 @@ def main():
     if rank == 0:
         # kernels of libbevr.so launched inside the timed device-resident region: msda_fwd + msda_bwd (sorted) per step,
         # plus the bf16 cast kernel; the cudaMemsetAsync zero-fill of grad_value is a driver memset, not one of ours
-        n_k = 2 if dt == 0 else 3
+        n_k = 2 if (dt == 0 or bwd_flags) else 3
         line = {"metric": METRIC, "value": value, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
                 "warmup": warm, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32" if dt == 0 else "bf16", "data": "synthetic",
-                "config": workload_config(B, args.dtype), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+                "config": dict(workload_config(B, args.dtype), grad_value="fp32 main gradients (BEVR_GRAD_VALUE_F32)"
+                               if bwd_flags else "storage dtype"), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": args.steps * n_k, "train": train, "k3": k3, "k5": k5, "config1": config1,
                 "clocks": clk.summary()}
         emit(line)

@@ -388,12 +388,17 @@ __global__ void __launch_bounds__(256, MSDA_BWD_MINB) msda_bwd_kernel(const __gr
 //      to the left (2 REDs + 2 row loads instead of 4 + 4); REDs are issued per RUN, not per tap: ~5x fewer;
 //   4. grad_loc / grad_weight are staged in shared memory by point id and written coalesced.
 // A CTA whose bounding boxes do not fit the histogram (offsets spread over > MAXBINS pixels) runs bwd_direct_tile.
+#ifndef MSDA_SORT_UNROLL
+#define MSDA_SORT_UNROLL 1         // unroll of the record walk
+#endif
 #ifndef MSDA_SORT_MINB
 #define MSDA_SORT_MINB 3           // resident CTAs per SM the register budget is set for (4 channels per lane)
 #endif
 #ifndef MSDA_SORT_MINB8
 #define MSDA_SORT_MINB8 2          // ... with 8 channels per lane (twice the register-resident rows)
 #endif
+
+constexpr int RUNCLS = 32;   // run-length classes of the sorted backward: 1 .. 31 records, and "32 or more"
 
 struct SortLvl {        // per level, in shared memory
   int xmin, ymin, xmax, ymax;   // bounding box of the nw pixels (x0 in [-1, W-1], y0 in [-1, H-1])
@@ -504,15 +509,18 @@ __global__ void __launch_bounds__(256, (NV == 8 ? MSDA_SORT_MINB8 : MSDA_SORT_MI
   float4* s_go = reinterpret_cast<float4*>(s_tmp + NP);  // [tq][row4] grad_out rows, fp32
   uint2* s_key = reinterpret_cast<uint2*>(s_go + (go_smem ? tq * row4 : 0));   // [NP] sorted: {pixel, point | mask | level}
   unsigned* s_hist = reinterpret_cast<unsigned*>(s_key + NP);                 // [maxbins + 1]
-  unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_hist + maxbins + 1);   // [NP]
+  unsigned* s_rt = s_hist + maxbins + 4;                                      // [NP] run table {first record | length << 16}
+  unsigned short* s_rank = reinterpret_cast<unsigned short*>(s_rt + NP);      // [NP]
   SortLvl* s_lvl = reinterpret_cast<SortLvl*>(reinterpret_cast<char*>(smem) + a.sort_lvl_off);     // [L]
-  int* s_misc = reinterpret_cast<int*>(s_lvl + BEVR_MAX_LEVELS);               // [0] nbins or -1 (overflow); [8..16) warp sums
+  int* s_misc = reinterpret_cast<int*>(s_lvl + BEVR_MAX_LEVELS);   // [0] nbins or -1 (overflow), [1] runs; [8..16) warp sums
+  unsigned* s_h2 = reinterpret_cast<unsigned*>(s_misc + 16);       // [RUNCLS + 1] runs per length class, then class offsets
 
   const TileCtx c = tile_ctx(a);
   const int vec_per_pix = a.h * a.Dh / NV;
 
   // ---- 0. initialise the boxes / histogram, stage the tile's grad_out rows
-  for (int i = tid; i <= maxbins; i += 256) s_hist[i] = 0u;
+  for (int i = tid; i <= maxbins / 4; i += 256) reinterpret_cast<uint4*>(s_hist)[i] = make_uint4(0u, 0u, 0u, 0u);
+  if (tid <= RUNCLS) s_h2[tid] = 0u;
   if (tid < a.L) {
     SortLvl& lv = s_lvl[tid];
     lv.xmin = lv.ymin = INT_MAX; lv.xmax = lv.ymax = INT_MIN;
@@ -636,103 +644,128 @@ __global__ void __launch_bounds__(256, (NV == 8 ? MSDA_SORT_MINB8 : MSDA_SORT_MI
   }
   __syncthreads();
 
-  // ---- 3. segmented reduction over the sorted records
+  // ---- 2d. run table.  A "run" = the records of one non-empty bin (same nw pixel).  The walk of step 3 keeps a run's
+  //          value rows and accumulators in registers, and a warp walks GPW runs side by side: to keep its control flow
+  //          UNIFORM (the first version let every group switch runs on its own: the divergent switch path ran in ~90 %
+  //          of the iterations and was half of all instructions) the runs are counting-sorted by LENGTH, longest first,
+  //          so that the runs a warp walks together have the same number of records.
   {
-    const int n = (int)s_hist[nbins];
-    const int grp = tid / LPG, lig = tid % LPG;
-    const int chunk = ((n + NG - 1) / NG) | 1;           // odd: the groups of a warp read records in distinct banks
-    const int r0 = min(grp * chunk, n), r1 = min(r0 + chunk, n);
+    unsigned* scratch = reinterpret_cast<unsigned*>(s_tmp);                    // the unsorted records are dead now
+    for (int b = tid; b < nbins; b += 256) {
+      const unsigned cnt = s_hist[b + 1] - s_hist[b];
+      if (cnt) scratch[b] = atomicAdd(&s_h2[min(cnt, (unsigned)RUNCLS)], 1u);
+    }
+    __syncthreads();
+    if (warp == 0) {                                     // class offsets, longest class first: lane <-> length lane + 1
+      const unsigned v = s_h2[lane + 1];
+      unsigned inc = v;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const unsigned u = __shfl_down_sync(0xffffffffu, inc, d);
+        if (lane + d < 32) inc += u;
+      }
+      s_h2[lane + 1] = inc - v;                          // runs longer than this class
+      if (lane == 0) s_misc[1] = (int)inc;               // number of runs
+    }
+    __syncthreads();
+    for (int b = tid; b < nbins; b += 256) {
+      const unsigned st = s_hist[b], cnt = s_hist[b + 1] - st;
+      if (cnt) s_rt[s_h2[min(cnt, (unsigned)RUNCLS)] + scratch[b]] = st | (cnt << 16);
+    }
+    __syncthreads();
+  }
+
+  // ---- 3. segmented reduction: a group of LPG lanes (one channel row) takes one run, the GPW groups of a warp take
+  //         GPW runs of (nearly) equal length; everything about a run is uniform across the warp
+  {
+    constexpr int GPW = 32 / LPG;
+    const int nruns = s_misc[1];
+    const int gw = lane / LPG, lig = lane % LPG;
     const size_t vec0 = (size_t)c.b * a.S * vec_per_pix + c.head * LPG + lig;
     const char* vbase = opaque(reinterpret_cast<const char*>(a.value) + vec0 * VB);
     const char* gvbase = a.grad_value ? opaque(reinterpret_cast<const char*>(a.grad_value) + vec0 * (NV * 4)) : nullptr;
     float* s_dot = reinterpret_cast<float*>(s_tmp);
+    const unsigned dx = (unsigned)vec_per_pix;
 
-    float2 val[4][H2], acc[4][H2];                       // the run's 2x2 value rows / grad_value accumulators
-    unsigned off[4] = {0u, 0u, 0u, 0u};
-    unsigned cm = 0u;                                    // bit t: tap t of the current run is inside its level
-    unsigned cur = 0x7fffffffu;                          // pixel of the current run's nw tap (never a real one)
-#pragma unroll
-    for (int t = 0; t < 4; ++t)
-#pragma unroll
-      for (int j = 0; j < H2; ++j) val[t][j] = acc[t][j] = make_float2(0.f, 0.f);
-
-    auto flush = [&]() {
-      if (!gvbase) return;
+    // rounds of 8 batches (one per warp), longest runs first; the warp order alternates from round to round so that no
+    // warp collects the longest batch of every round
+    for (int round = 0; round * 8 * GPW < nruns; ++round) {            // warp-uniform
+      const int base = (round * 8 + ((round & 1) ? 7 - warp : warp)) * GPW;
+      if (base >= nruns) continue;
+      const int ri = base + gw;
+      const unsigned rd = ri < nruns ? s_rt[ri] : 0u;
+      const int start = (int)(rd & 0xffffu), cnt = (int)(rd >> 16);
+      const int maxc = __reduce_max_sync(0xffffffffu, cnt);
+      const uint2 k0 = cnt ? s_key[start] : make_uint2(0u, 0u);
+      const unsigned m = cnt ? ((k0.y >> 13) & 15u) : 0u;              // taps of the run that lie inside the level
+      const unsigned dy = s_lvl[(k0.y >> 17) & 7u].dy_vec;
+      const unsigned o0 = k0.x * dx;                     // wraps for x0 = -1 / y0 = -1; such taps are never dereferenced
+      const unsigned off[4] = {o0, o0 + dx, o0 + dy, o0 + dy + dx};
+      float2 val[4][H2], acc[4][H2];
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        float* dst = reinterpret_cast<float*>(const_cast<char*>(addr_u32(gvbase, off[t], NV * 4)));
 #pragma unroll
-        for (int j = 0; j < NV / 4; ++j)
-          red_add_v4_if((cm >> t) & 1u, dst + 4 * j, acc[t][2 * j].x, acc[t][2 * j].y, acc[t][2 * j + 1].x, acc[t][2 * j + 1].y);
+        for (int j = 0; j < H2; ++j) val[t][j] = acc[t][j] = make_float2(0.f, 0.f);
+        if ((m >> t) & 1u) load_row<T, NV>(addr_u32(vbase, off[t], VB), val[t]);
       }
-    };
-
-    // every group runs the same number of iterations (uniform control flow around the full-mask shuffles); a group
-    // that has run out of records idles on a copy of its current run with zero weights
-    for (int it = 0; it < chunk; ++it) {
-      const int r = r0 + it;
-      const bool live = r < r1;
-      uint2 k = make_uint2(cur, cm << 13);
-      float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (live) { k = s_key[r]; w = s_w[r]; }
-      const unsigned m = (k.y >> 13) & 15u;
-      if (k.x != cur || m != cm) {                       // new run: flush the accumulators, fetch the new value rows
-        flush();
-        const unsigned dy = s_lvl[(k.y >> 17) & 7u].dy_vec, dx = (unsigned)vec_per_pix;
-        const unsigned base = k.x * dx;                  // wraps for x0 = -1 / y0 = -1; such taps are never dereferenced
-        off[0] = base; off[1] = base + dx; off[2] = base + dy; off[3] = base + dy + dx;
+_Pragma(MSDA_STR(unroll MSDA_SORT_UNROLL))
+      for (int it = 0; it < maxc; ++it) {
+        const bool live = it < cnt;
+        unsigned ky = 0u;
+        float4 w = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live) { ky = s_key[start + it].y; w = s_w[start + it]; }
+        const int src = (int)(ky & 0x1fffu);
+        float2 g[H2];
+        if (go_smem) {
+          const float4* gp = s_go + point_q(src) * row4 + lig * (NV / 4);
+#pragma unroll
+          for (int j = 0; j < NV / 4; ++j) {
+            const float4 g4 = gp[j];
+            g[2 * j] = make_float2(g4.x, g4.y); g[2 * j + 1] = make_float2(g4.z, g4.w);
+          }
+        } else {                                         // few points per query (L*P small): each row is used once or twice
+          int q;
+          tile_query(a, c, point_q(src), q);
+          load_row<T, NV>(reinterpret_cast<const char*>(a.grad_out) +
+                          ((((size_t)c.b * a.Nq + q) * a.h + c.head) * LPG + lig) * VB, g);
+        }
+        const float wt[4] = {w.x, w.y, w.z, w.w};
+        float d[4];
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {                    // packed FFMA2: 5 issue slots per tap and 4 channels instead of 8
+          float2 s2 = __fmul2_rn(g[0], val[t][0]);
+#pragma unroll
+          for (int j = 1; j < H2; ++j) s2 = __ffma2_rn(g[j], val[t][j], s2);
+          d[t] = s2.x + s2.y;
+          const float2 w2 = make_float2(wt[t], wt[t]);
+#pragma unroll
+          for (int j = 0; j < H2; ++j) acc[t][j] = __ffma2_rn(w2, g[j], acc[t][j]);
+        }
+        // <grad_out, value row> of the four taps, summed over the group's lanes; step 4 turns them into gradients
+        if constexpr (LPG == 2) {
+          const bool hi = lig & 1;
+          float ka = hi ? d[2] : d[0], kb = hi ? d[3] : d[1];
+          ka += __shfl_xor_sync(0xffffffffu, hi ? d[0] : d[2], 1);
+          kb += __shfl_xor_sync(0xffffffffu, hi ? d[1] : d[3], 1);
+          if (live) { s_dot[src * 4 + 2 * hi] = ka; s_dot[src * 4 + 2 * hi + 1] = kb; }
+        } else if constexpr (LPG == 1) {
+          if (live) reinterpret_cast<float4*>(s_dot)[src] = make_float4(d[0], d[1], d[2], d[3]);
+        } else {
+          int which;
+          const float sum = group_sum4<LPG>(d[0], d[1], d[2], d[3], lig, which);
+          if (live && which >= 0) s_dot[src * 4 + which] = sum;
+        }
+      }
+      if (gvbase) {                                      // one vector reduction per value row of the RUN, not per tap
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
+          float* dst = reinterpret_cast<float*>(const_cast<char*>(addr_u32(gvbase, off[t], NV * 4)));
 #pragma unroll
-          for (int j = 0; j < H2; ++j) val[t][j] = acc[t][j] = make_float2(0.f, 0.f);
-          if ((m >> t) & 1u) load_row<T, NV>(addr_u32(vbase, off[t], VB), val[t]);
+          for (int j = 0; j < NV / 4; ++j)
+            red_add_v4_if((m >> t) & 1u, dst + 4 * j, acc[t][2 * j].x, acc[t][2 * j].y, acc[t][2 * j + 1].x, acc[t][2 * j + 1].y);
         }
-        cm = m;
-        cur = k.x;
-      }
-      const int src = (int)(k.y & 0x1fffu);
-      float2 g[H2];
-      if (go_smem) {
-        const float4* gp = s_go + point_q(src) * row4 + lig * (NV / 4);
-#pragma unroll
-        for (int j = 0; j < NV / 4; ++j) {
-          const float4 g4 = gp[j];
-          g[2 * j] = make_float2(g4.x, g4.y); g[2 * j + 1] = make_float2(g4.z, g4.w);
-        }
-      } else {                                           // few points per query (L*P small): each row is used once or twice
-        int q;
-        tile_query(a, c, point_q(src), q);
-        load_row<T, NV>(reinterpret_cast<const char*>(a.grad_out) +
-                        ((((size_t)c.b * a.Nq + q) * a.h + c.head) * LPG + lig) * VB, g);
-      }
-      const float wt[4] = {w.x, w.y, w.z, w.w};
-      float d[4];
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {                      // packed FFMA2: 5 issue slots per tap and 4 channels instead of 8
-        float2 s2 = __fmul2_rn(g[0], val[t][0]);
-#pragma unroll
-        for (int j = 1; j < H2; ++j) s2 = __ffma2_rn(g[j], val[t][j], s2);
-        d[t] = s2.x + s2.y;
-        const float2 w2 = make_float2(wt[t], wt[t]);
-#pragma unroll
-        for (int j = 0; j < H2; ++j) acc[t][j] = __ffma2_rn(w2, g[j], acc[t][j]);
-      }
-      // <grad_out, value row> of the four taps, summed over the group's lanes; step 4 turns them into gradients
-      if constexpr (LPG == 2) {
-        const bool hi = lig & 1;
-        float ka = hi ? d[2] : d[0], kb = hi ? d[3] : d[1];
-        ka += __shfl_xor_sync(0xffffffffu, hi ? d[0] : d[2], 1);
-        kb += __shfl_xor_sync(0xffffffffu, hi ? d[1] : d[3], 1);
-        if (live) { s_dot[src * 4 + 2 * hi] = ka; s_dot[src * 4 + 2 * hi + 1] = kb; }
-      } else if constexpr (LPG == 1) {
-        if (live) reinterpret_cast<float4*>(s_dot)[src] = make_float4(d[0], d[1], d[2], d[3]);
-      } else {
-        int which;
-        const float sum = group_sum4<LPG>(d[0], d[1], d[2], d[3], lig, which);
-        if (live && which >= 0) s_dot[src * 4 + which] = sum;
       }
     }
-    flush();
   }
   __syncthreads();
 
@@ -892,10 +925,10 @@ static int launch_sorted(MsdaArgs& a, cudaStream_t st) {
   const int LP = a.L * a.P, tq = a.th << a.tw_shift, NP = tq * LP, row4 = a.Dh / 4;
   const int maxbins = MSDA_SORT_MAXBINS;
   a.sort_go_smem = (size_t)tq * row4 * 16 <= MSDA_SORT_GO_BYTES;
-  size_t bytes = (size_t)NP * 40 + (a.sort_go_smem ? (size_t)tq * row4 * 16 : 0) + (size_t)(maxbins + 1) * 4 + (size_t)NP * 2;
+  size_t bytes = (size_t)NP * 44 + (a.sort_go_smem ? (size_t)tq * row4 * 16 : 0) + (size_t)(maxbins + 4) * 4 + (size_t)NP * 2;
   bytes = (bytes + 15) & ~(size_t)15;
   a.sort_lvl_off = (int)bytes;
-  bytes += BEVR_MAX_LEVELS * sizeof(SortLvl) + 16 * sizeof(int);
+  bytes += BEVR_MAX_LEVELS * sizeof(SortLvl) + (16 + RUNCLS + 2) * sizeof(int);
   const size_t direct = (size_t)8 * 2 * (32 / ((LPG * NV) / 4)) * (LP + 1) * 16;     // staging of the per-CTA fallback
   BEVR_REQUIRE(direct <= (size_t)a.sort_lvl_off, "msda_bwd: L*P=%d too large for the sorted backward", LP);
   BEVR_REQUIRE(bytes <= 200 * 1024, "msda_bwd: sorted backward needs %zu B of shared memory", bytes);
@@ -971,13 +1004,15 @@ extern "C" int bevr_msda_bwd(const void* value, const int32_t* spatial_hw, const
   if (B == 0) return 0;
   if (Nq == 0) {                                   // no queries: grad_value is all zeros, nothing else to write
     if (grad_value && !(flags & BEVR_ACCUMULATE))
-      return check_cuda(cudaMemsetAsync(grad_value, 0, (size_t)B * S * h * Dh * (dtype == BEVR_F32 ? 4 : 2),
+      return check_cuda(cudaMemsetAsync(grad_value, 0, (size_t)B * S * h * Dh *
+                                        ((dtype == BEVR_F32 || (flags & BEVR_GRAD_VALUE_F32)) ? 4 : 2),
                                         (cudaStream_t)stream), "msda_bwd zero-fill");
     return 0;
   }
   BEVR_REQUIRE(value && sampling_loc && grad_out, "msda_bwd: value / sampling_loc / grad_out must not be NULL");
   BEVR_REQUIRE(!(attn_weight == nullptr && grad_weight != nullptr), "msda_bwd: grad_weight without attn_weight");
-  BEVR_REQUIRE(!(dtype == BEVR_BF16 && grad_value && !workspace), "msda_bwd: bf16 grad_value needs the fp32 workspace");
+  const bool gv_f32 = dtype == BEVR_F32 || (flags & BEVR_GRAD_VALUE_F32);       // grad_value buffer holds fp32
+  BEVR_REQUIRE(!(!gv_f32 && grad_value && !workspace), "msda_bwd: bf16 grad_value needs the fp32 workspace");
   BEVR_REQUIRE(!(a.nchunk > 1 && dtype == BEVR_BF16 && grad_weight),
                "msda_bwd: bf16 grad_weight with Dh > 128 is not supported");
   cudaStream_t st = (cudaStream_t)stream;
@@ -986,9 +1021,9 @@ extern "C" int bevr_msda_bwd(const void* value, const int32_t* spatial_hw, const
   const size_t n = (size_t)B * S * h * Dh;
   a.grad_value = nullptr;
   if (grad_value) {
-    a.grad_value = dtype == BEVR_F32 ? (float*)grad_value : (float*)workspace;
-    // bf16: the fp32 workspace always starts at zero; BEVR_ACCUMULATE is honoured by the cast kernel below
-    if (!(flags & BEVR_ACCUMULATE) || dtype == BEVR_BF16)
+    a.grad_value = gv_f32 ? (float*)grad_value : (float*)workspace;
+    // bf16 output: the fp32 workspace always starts at zero; BEVR_ACCUMULATE is honoured by the cast kernel below
+    if (!(flags & BEVR_ACCUMULATE) || !gv_f32)
       if (int rc = check_cuda(cudaMemsetAsync(a.grad_value, 0, n * sizeof(float), st), "msda_bwd zero-fill")) return rc;
   }
   if (a.nchunk > 1) {  // chunks accumulate with atomics -> outputs must start at zero
@@ -1002,7 +1037,7 @@ extern "C" int bevr_msda_bwd(const void* value, const int32_t* spatial_hw, const
   if (direct) rc = dtype == BEVR_F32 ? dispatch_bwd<float>(a, st) : dispatch_bwd<__nv_bfloat16>(a, st);
   else rc = dtype == BEVR_F32 ? dispatch_bwd_sorted<float>(a, st) : dispatch_bwd_sorted<__nv_bfloat16>(a, st);
   if (rc) return rc;
-  if (grad_value && dtype == BEVR_BF16) {
+  if (grad_value && !gv_f32) {
     cast_f32_to_bf16_kernel<<<sm_count() * 8, 256, 0, st>>>((const float4*)workspace, (uint2*)grad_value, n / 4,
                                                                (flags & BEVR_ACCUMULATE) ? 1 : 0);
     return check_launch("msda_bwd cast");

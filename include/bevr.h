@@ -42,8 +42,11 @@ enum {
   BEVR_OFFSET_PIXELS   = 4,  /* with ref_points: loc = ref + off / (W_l, H_l); else loc = ref + off    */
   BEVR_ACCUMULATE      = 8,  /* bwd: add into grad_value instead of overwriting it (fp32: the REDs land on
                                 the caller's contents; bf16: the final cast adds them in fp32)            */
-  BEVR_BWD_DIRECT      = 16  /* msda_bwd: one RED per tap (round-1 kernel) instead of the tile-sorted
+  BEVR_BWD_DIRECT      = 16, /* msda_bwd: one RED per tap (round-1 kernel) instead of the tile-sorted
                                 backward; the default picks the sorted kernel whenever Dh <= 128         */
+  BEVR_GRAD_VALUE_F32  = 32  /* msda_bwd, dtype = bf16: grad_value is a FLOAT32 (B, S, h, Dh) buffer (fp32
+                                main gradients of mixed-precision training): the reductions land in it
+                                directly, no workspace, no zero-filled copy, no cast pass                */
 };
 
 #define BEVR_MAX_LEVELS 8

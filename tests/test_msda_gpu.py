@@ -277,3 +277,26 @@ def test_backward_accumulate_flag(dtype):
     torch.cuda.synchronize()
     assert float(once.abs().max()) > 0
     assert rel_err(gv.float(), 2 * once.float()) < (1e-6 if dt == 0 else 1e-2)
+
+
+def test_bf16_with_fp32_main_gradient_flag():
+    """BEVR_GRAD_VALUE_F32: bf16 storage, grad_value delivered in fp32 straight from the reductions (no workspace, no
+    cast); equals the bf16-output path before its final rounding."""
+    import ctypes as C
+    from bevrender_b200 import _lib
+    d = make_microbench_inputs(1, seed=12, n_side=16, h=2, Dh=32, L=2, P=4)
+    dev = "cuda"
+    v, w, go = (d[k].to(dev).to(torch.bfloat16).contiguous() for k in ("value", "attention_weights", "grad_out"))
+    loc = d["sampling_locations"].to(dev).contiguous()
+    B, S, h, Dh = v.shape
+    Nq, L, P = loc.shape[1], loc.shape[3], loc.shape[4]
+    hw = (C.c_int32 * (2 * L))(*[x for s in d["spatial_shapes"] for x in s])
+    st = (C.c_int32 * L)(*d["level_start_index"])
+    P_ = lambda t: C.c_void_p(t.data_ptr())
+    gv32 = torch.full((B, S, h, Dh), float("nan"), dtype=torch.float32, device=dev)
+    flags = (16 if BWD_DIRECT else 0) | 32
+    _lib.check(_lib.lib().bevr_msda_bwd(P_(v), hw, st, P_(loc), None, P_(w), P_(go), P_(gv32), None, None, None, B, S, h, Dh,
+                                        Nq, L, P, 16, 1, flags, None), "bevr_msda_bwd")
+    ref = omsda.msda_forward_backward(v.float().cpu(), d["spatial_shapes"], d["level_start_index"], d["sampling_locations"],
+                                      w.float().cpu(), go.float().cpu())
+    assert rel_err(gv32.cpu(), ref[1]) < FP32_TOL          # fp32 accumulation of bf16-rounded inputs: fp32-grade
