@@ -29,6 +29,7 @@ SIGNATURES = {
     "bevr_rpe_attn_workspace_bytes": (_z, [_i] * 8),
     "bevr_rpe_attn_fwd": (_i, [_p] * 8 + [_i] * 9 + [_f, _i, _p]),
     "bevr_rpe_attn_bwd": (_i, [_p] * 15 + [_i] * 9 + [_f, _i, _p]),
+    "bevr_recall_ranks": (_i, [_p, _p, _i, _p]),
     "bevr_offset_head_fwd": (_i, [_p] * 5 + [C.c_longlong, _p, _p] + [_i] * 7 + [_f, _f, _p]),
     "bevr_offset_head_bwd": (_i, [_p] * 5 + [C.c_longlong] + [_p] * 6 + [_i] * 7 + [_f, _f, _p]),
 }

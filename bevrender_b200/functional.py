@@ -309,19 +309,26 @@ def project_history_bev(bev, vehicle_pose):
 
 
 @torch.no_grad()
-def retrieval_recall(camera_embed, map_embed, ks=(1, 5, 10)):
-    """Recall@k of the retrieval metric ("next" row f-4; Trainer.get_recall, train.py:551-572), on the device.
-
-    dist = 2 - 2 * X @ Y^T (a plain cuBLAS GEMM in fp32); for every column k the rank of the true match is the
-    number of rows with dist[:, k] < dist[k, k]; recall@i = 100 * mean(rank < i).  The reference evaluates this
-    with numpy and an O(11 * N) Python loop on the host.
-    """
+def retrieval_ranks(camera_embed, map_embed):
+    """rank[k] = #{r : dist[r, k] < dist[k, k]} with dist = 2 - 2 X Y^T: the GEMM is a plain cuBLAS call in fp32 (ranks
+    are discontinuous in dist: no TF32), the counting loop of Trainer.get_recall (train.py:559-566) is one kernel."""
     _need_cuda(camera_embed, map_embed)
     prev = torch.backends.cuda.matmul.allow_tf32
-    torch.backends.cuda.matmul.allow_tf32 = False            # ranks are discontinuous in dist: keep fp32 products
+    torch.backends.cuda.matmul.allow_tf32 = False
     try:
-        dist = 2.0 - 2.0 * (camera_embed.float() @ map_embed.float().T)
+        dist = (2.0 - 2.0 * (camera_embed.float() @ map_embed.float().T)).contiguous()
     finally:
         torch.backends.cuda.matmul.allow_tf32 = prev
-    rank = (dist < dist.diagonal()[None, :]).sum(0)
+    n = dist.shape[0]
+    rank = torch.empty(n, dtype=torch.int32, device=dist.device)
+    _lib.check(_lib.lib().bevr_recall_ranks(_ptr(dist), _ptr(rank), n, _stream()), "bevr_recall_ranks")
+    return rank
+
+
+@torch.no_grad()
+def retrieval_recall(camera_embed, map_embed, ks=(1, 5, 10)):
+    """Recall@k of the retrieval metric ("next" row f-4; Trainer.get_recall, train.py:551-572), on the device:
+    recall@i = 100 * mean(rank < i) with the ranks of ``retrieval_ranks``.  The reference evaluates this with numpy and an
+    O(11 * N) Python loop on the host."""
+    rank = retrieval_ranks(camera_embed, map_embed)
     return tuple(float((rank < k).float().mean() * 100) for k in ks)

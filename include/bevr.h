@@ -202,6 +202,14 @@ int bevr_offset_head_bwd(const float* y, const float* ln_weight, const float* ln
                          float* grad_w1, int Bg, int Cm, int H, int W, int O, int interleave, int scaled,
                          float factor, float eps, void* stream);
 
+/* ---------------------------------------------------------------------------
+ * Retrieval-recall ranks ("next" row f-4): the counting loop of Trainer.get_recall (train.py:551-572).
+ *   dist  dev f32 (n, n)  row-major distances, 2 - 2 X Y^T (the caller forms it with a library GEMM)
+ *   rank  dev i32 (n)     OVERWRITTEN: rank[k] = #{ r : dist[r, k] < dist[k, k] }   (strict, as the reference)
+ * recall@i = 100 * mean(rank < i).
+ */
+int bevr_recall_ranks(const float* dist, int32_t* rank, int n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

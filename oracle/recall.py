@@ -1,6 +1,7 @@
 """Oracle for the retrieval recall metric ("next" row f-4): numpy restatement of ``Trainer.get_recall``
-(train.py:551-572).  ``train.py`` itself cannot be imported (pytorch_metric_learning / yourdfpy missing), so this
-function is pinned only by construction ("parity unpinned" for this row): same formula, same strict ``<``."""
+(train.py:551-572).  ``train.py`` itself cannot be imported (pytorch_metric_learning / yourdfpy missing); the method
+is numpy-only, so ``tests/golden/make_golden.py`` cuts it out of train.py with ``ast``, runs it, and commits its output
+as ``tests/golden/recall.npz``: this restatement is pinned against that (``tests/test_recall.py``)."""
 import numpy as np
 
 

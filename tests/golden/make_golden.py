@@ -263,6 +263,33 @@ def main():
     make_proj("proj_yaw", 56, 5, bound, -1.0, 75.0, 10.0)          # most points off-image / behind
     make_proj("proj_z0", 28, 4, {"X": 20.0, "Y": 10.0, "Z": 2.0}, 1.0, 90.0, 0.0)  # z_cam == 0 rows
     make_proj_gray("proj_gray")
+    make_recall("recall")
+
+
+def reference_get_recall():
+    """``Trainer.get_recall`` (train.py:551-572) lifted out of train.py WITHOUT importing the module (its imports need
+    pytorch_metric_learning / yourdfpy): the method's source is cut out with ``ast`` and compiled on its own; it only
+    uses numpy."""
+    import ast
+    src = open(os.path.join(REF, "train.py")).read()
+    tree = ast.parse(src)
+    fn = next(n for cls in tree.body if isinstance(cls, ast.ClassDef) and cls.name == "Trainer"
+              for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == "get_recall")
+    mod = ast.Module(body=[fn], type_ignores=[])
+    ns = {"np": np}
+    exec(compile(mod, "train.py:get_recall", "exec"), ns)
+    return lambda cam, maps: ns["get_recall"](None, cam, maps)
+
+
+def make_recall(name="recall"):
+    rng = np.random.default_rng(0)
+    maps = rng.standard_normal((96, 64)).astype(np.float32)
+    maps /= np.linalg.norm(maps, axis=1, keepdims=True)
+    cam = maps + 0.45 * rng.standard_normal(maps.shape).astype(np.float32)
+    cam /= np.linalg.norm(cam, axis=1, keepdims=True)
+    r = reference_get_recall()(cam, maps)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), camera=cam, maps=maps, recall=np.array(r, dtype=np.float64))
+    print(name, "recall@1/5/10", r)
 
 
 if __name__ == "__main__":
