@@ -398,6 +398,10 @@ __global__ void __launch_bounds__(256, MSDA_BWD_MINB) msda_bwd_kernel(const __gr
 #define MSDA_SORT_MINB8 2          // ... with 8 channels per lane (twice the register-resident rows)
 #endif
 
+#ifndef MSDA_SORT_BATCH
+#define MSDA_SORT_BATCH 4          // points per thread whose coordinate loads are issued together in the per-point steps
+#endif
+
 constexpr int RUNCLS = 32;   // run-length classes of the sorted backward: 1 .. 31 records, and "32 or more"
 
 struct SortLvl {        // per level, in shared memory
@@ -409,19 +413,29 @@ struct SortLvl {        // per level, in shared memory
   float sx, sy;                 // d pixel / d location
 };
 
+// raw operands of one sampling point (location, reference point, weight): loads only, so that a thread can have the
+// loads of several points in flight before it touches the first one
+struct PointRaw {
+  float2 xy, r;
+  float aw;
+};
 template <typename T>
-__device__ __forceinline__ bool point_coords(const MsdaArgs& a, size_t item, int bq, int p, int l, float& px, float& py,
-                                             float& aw) {
-  const int LP = a.L * a.P;
+__device__ __forceinline__ PointRaw point_load(const MsdaArgs& a, size_t item, int bq, int p, int l) {
+  PointRaw o;
+  const size_t li = item * (a.L * a.P) + p;
+  o.xy = __ldg(reinterpret_cast<const float2*>(a.loc) + li);
+  o.r = make_float2(0.f, 0.f);
+  if (a.ref) o.r = __ldg(reinterpret_cast<const float2*>(a.ref) + (size_t)bq * a.L + l);
+  o.aw = a.weight ? load_scalar(reinterpret_cast<const T*>(a.weight) + li) : 1.f;
+  return o;
+}
+__device__ __forceinline__ bool point_finish(const MsdaArgs& a, const PointRaw& o, int l, float& px, float& py) {
   const int H = a.lvl_h[l], W = a.lvl_w[l];
-  const size_t li = item * LP + p;
-  float2 xy = __ldg(reinterpret_cast<const float2*>(a.loc) + li);
+  float2 xy = o.xy;
   if (a.ref) {
-    const float2 r = __ldg(reinterpret_cast<const float2*>(a.ref) + (size_t)bq * a.L + l);
     if (a.flags & BEVR_OFFSET_PIXELS) { xy.x = xy.x / (float)W; xy.y = xy.y / (float)H; }
-    xy.x += r.x; xy.y += r.y;
+    xy.x += o.r.x; xy.y += o.r.y;
   }
-  aw = a.weight ? load_scalar(reinterpret_cast<const T*>(a.weight) + li) : 1.f;
   px = unnormalize(xy.x, W, a.flags); py = unnormalize(xy.y, H, a.flags);
   return (px > -1.f) && (px < (float)W) && (py > -1.f) && (py < (float)H);     // false for NaN / inf
 }
@@ -546,28 +560,44 @@ __global__ void __launch_bounds__(256, (NV == 8 ? MSDA_SORT_MINB8 : MSDA_SORT_MI
   // ---- 1. points -> unsorted records + per-level bounding boxes.  The box is grown with shared atomics, but a thread
   //         only issues one when its point lies outside the box it reads first: after the first few points of a tile
   //         almost none do.
-  for (int i = tid; i < NP; i += 256) {
-    uint4 rec = make_uint4(0u, 0u, 0u, 0u);              // invalid point (no record; step 4 writes zero gradients)
-    const int qi = point_q(i);
-    const int p = i - qi * LP;
-    int q;
-    if (tile_query(a, c, qi, q)) {
-      const int bq = c.b * a.Nq + q;
-      const int l = point_l(p);
-      float px, py, aw;
-      if (point_coords<T>(a, (size_t)bq * a.h + c.head, bq, p, l, px, py, aw)) {
+  for (int i0 = tid; i0 < NP; i0 += 256 * MSDA_SORT_BATCH) {
+    PointRaw raw[MSDA_SORT_BATCH];
+    int lv_of[MSDA_SORT_BATCH];                          // level, or -1: no such point / query outside the grid
+#pragma unroll
+    for (int k = 0; k < MSDA_SORT_BATCH; ++k) {          // all loads first: one round trip per batch, not per point
+      const int i = i0 + 256 * k;
+      lv_of[k] = -1;
+      if (i < NP) {
+        const int qi = point_q(i);
+        const int p = i - qi * LP;
+        int q;
+        if (tile_query(a, c, qi, q)) {
+          const int bq = c.b * a.Nq + q;
+          lv_of[k] = point_l(p);
+          raw[k] = point_load<T>(a, (size_t)bq * a.h + c.head, bq, p, lv_of[k]);
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < MSDA_SORT_BATCH; ++k) {
+      const int i = i0 + 256 * k;
+      if (i >= NP) break;
+      uint4 rec = make_uint4(0u, 0u, 0u, 0u);            // invalid point (no record; step 4 writes zero gradients)
+      const int l = lv_of[k];
+      float px, py;
+      if (l >= 0 && point_finish(a, raw[k], l, px, py)) {
         const float x0f = floorf(px), y0f = floorf(py);
         const int x0 = (int)x0f, y0 = (int)y0f;
         rec = make_uint4(0x80000000u | ((unsigned)(y0 + 1) << 15) | (unsigned)(x0 + 1), __float_as_uint(px - x0f),
-                         __float_as_uint(py - y0f), __float_as_uint(aw));
+                         __float_as_uint(py - y0f), __float_as_uint(raw[k].aw));
         SortLvl& lv = s_lvl[l];
         if (x0 < lv.xmin) atomicMin(&lv.xmin, x0);
         if (x0 > lv.xmax) atomicMax(&lv.xmax, x0);
         if (y0 < lv.ymin) atomicMin(&lv.ymin, y0);
         if (y0 > lv.ymax) atomicMax(&lv.ymax, y0);
       }
+      s_tmp[i] = rec;
     }
-    s_tmp[i] = rec;
   }
   __syncthreads();
   if (tid == 0) {
@@ -771,25 +801,45 @@ _Pragma(MSDA_STR(unroll MSDA_SORT_UNROLL))
 
   // ---- 4. one thread per point again: dot products -> d/d location, d/d weight; coalesced writes.  The point's
   //         fractions and weight are recomputed from its (L1-resident) location rather than kept in shared memory.
-  for (int i = tid; i < NP; i += 256) {
-    const int qi = point_q(i);
-    const int p = i - qi * LP;
-    int q;
-    if (!tile_query(a, c, qi, q)) continue;
-    const int l = point_l(p);
-    const int bq = c.b * a.Nq + q;
-    const size_t item = (size_t)bq * a.h + c.head;
-    float px, py, aw, gw = 0.f, gx = 0.f, gy = 0.f;
-    if (point_coords<T>(a, item, bq, p, l, px, py, aw)) {   // same predicate as step 1: the point has a record
-      const float4 d = reinterpret_cast<const float4*>(s_tmp)[i];
-      const float wx1 = px - floorf(px), wy1 = py - floorf(py), wx0 = 1.f - wx1, wy0 = 1.f - wy1;
-      gw = wy0 * (wx0 * d.x + wx1 * d.y) + wy1 * (wx0 * d.z + wx1 * d.w);
-      gx = aw * (wy0 * (d.y - d.x) + wy1 * (d.w - d.z));
-      gy = aw * (wx0 * (d.z - d.x) + wx1 * (d.w - d.y));
+  for (int i0 = tid; i0 < NP; i0 += 256 * MSDA_SORT_BATCH) {
+    PointRaw raw[MSDA_SORT_BATCH];
+    int lv_of[MSDA_SORT_BATCH];
+    size_t li_of[MSDA_SORT_BATCH];
+#pragma unroll
+    for (int k = 0; k < MSDA_SORT_BATCH; ++k) {
+      const int i = i0 + 256 * k;
+      lv_of[k] = -1;
+      if (i < NP) {
+        const int qi = point_q(i);
+        const int p = i - qi * LP;
+        int q;
+        if (tile_query(a, c, qi, q)) {
+          const int bq = c.b * a.Nq + q;
+          const size_t item = (size_t)bq * a.h + c.head;
+          lv_of[k] = point_l(p);
+          li_of[k] = item * LP + p;
+          raw[k] = point_load<T>(a, item, bq, p, lv_of[k]);
+        }
+      }
     }
-    const size_t li = item * LP + p;
-    if (a.grad_loc) reinterpret_cast<float2*>(a.grad_loc)[li] = make_float2(gx * s_lvl[l].sx, gy * s_lvl[l].sy);
-    if (a.grad_weight) store_scalar(reinterpret_cast<T*>(a.grad_weight) + li, gw);
+#pragma unroll
+    for (int k = 0; k < MSDA_SORT_BATCH; ++k) {
+      const int i = i0 + 256 * k;
+      const int l = lv_of[k];
+      if (l < 0) continue;
+      float px, py, gw = 0.f, gx = 0.f, gy = 0.f;
+      if (point_finish(a, raw[k], l, px, py)) {          // same predicate as step 1: the point has a record
+        const float aw = raw[k].aw;
+        const float4 d = reinterpret_cast<const float4*>(s_tmp)[i];
+        const float wx1 = px - floorf(px), wy1 = py - floorf(py), wx0 = 1.f - wx1, wy0 = 1.f - wy1;
+        gw = wy0 * (wx0 * d.x + wx1 * d.y) + wy1 * (wx0 * d.z + wx1 * d.w);
+        gx = aw * (wy0 * (d.y - d.x) + wy1 * (d.w - d.z));
+        gy = aw * (wx0 * (d.z - d.x) + wx1 * (d.w - d.y));
+      }
+      const size_t li = li_of[k];
+      if (a.grad_loc) reinterpret_cast<float2*>(a.grad_loc)[li] = make_float2(gx * s_lvl[l].sx, gy * s_lvl[l].sy);
+      if (a.grad_weight) store_scalar(reinterpret_cast<T*>(a.grad_weight) + li, gw);
+    }
   }
 }
 
