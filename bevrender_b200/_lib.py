@@ -29,6 +29,8 @@ SIGNATURES = {
     "bevr_rpe_attn_workspace_bytes": (_z, [_i] * 8),
     "bevr_rpe_attn_fwd": (_i, [_p] * 8 + [_i] * 9 + [_f, _i, _p]),
     "bevr_rpe_attn_bwd": (_i, [_p] * 15 + [_i] * 9 + [_f, _i, _p]),
+    "bevr_rpe_attn_fwd_dropout": (_i, [_p] * 8 + [_i] * 9 + [_f, _i, _f, C.c_ulonglong, _p]),
+    "bevr_rpe_attn_bwd_dropout": (_i, [_p] * 15 + [_i] * 9 + [_f, _i, _f, C.c_ulonglong, _p]),
     "bevr_recall_ranks": (_i, [_p, _p, _i, _p]),
     "bevr_offset_head_fwd": (_i, [_p] * 5 + [C.c_longlong, _p, _p] + [_i] * 7 + [_f, _f, _p]),
     "bevr_offset_head_bwd": (_i, [_p] * 5 + [C.c_longlong] + [_p] * 6 + [_i] * 7 + [_f, _f, _p]),
@@ -46,7 +48,7 @@ def build(force=False):
 
 
 _lib = None
-EXPECTED_VERSION = 200          # BEVR_VERSION of include/bevr.h; bumped with every signature change
+EXPECTED_VERSION = 210          # BEVR_VERSION of include/bevr.h; bumped with every signature change
 
 
 def _stale():

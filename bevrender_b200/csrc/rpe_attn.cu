@@ -39,6 +39,10 @@ struct RpeArgs {
   const float *kh, *kl, *vh, *vl, *qh, *ql, *gh, *gl;
   int NsP, NqP;
   float scale;
+  // attention dropout (TSA_deform_attn.py:313-323, SCA_deform_attn.py:402-410): keep mask from a counter-based hash
+  unsigned drop_thresh;      // 24-bit threshold: an element is dropped when hash >> 8 < drop_thresh (0: no dropout)
+  unsigned seed_lo, seed_hi;
+  float drop_scale;          // 1 / (1 - p)
 };
 
 // DH (channels per head) is a template parameter of every kernel: 32 (the reference, encoder.py:23-39) and 16.
@@ -101,6 +105,24 @@ __device__ __forceinline__ float rpe_bias(const float* tbl, const Bilin& b, int 
 __device__ __forceinline__ const float* opaque_f(const float* p) {
   asm volatile("" : "+l"(p));      // keep the per-thread table base in a register pair (1-instruction addressing)
   return p;
+}
+
+// Attention dropout.  The reference applies nn.Dropout to the softmax matrix, i.e. draws from torch's Philox stream over a
+// (B*h, Nq, Ns) tensor that is never materialised here; the kernels draw the keep mask from a counter-based hash of
+// (seed, b*h, query, key) instead -- the same distribution (Bernoulli(1 - p), kept elements scaled by 1 / (1 - p)), a
+// different stream.  The three kernels of a call regenerate the same mask; oracle/deform_attn.py restates the hash.
+__device__ __forceinline__ unsigned mix32(unsigned x) {
+  x ^= x >> 16; x *= 0x85ebca6bu; x ^= x >> 13; x *= 0xc2b2ae35u; x ^= x >> 16;
+  return x;
+}
+__device__ __forceinline__ unsigned drop_key(const unsigned seed_lo, const unsigned seed_hi, int bh) {
+  return mix32(seed_lo + (unsigned)bh * 0x9e3779b9u) ^ seed_hi;
+}
+// multiplier of probability (query i, key j): 0 or 1 / (1 - p); row_base = i * Ns (mod 2^32)
+template <bool DROP>
+__device__ __forceinline__ float drop_mul(unsigned thresh, float scale, unsigned key, unsigned row_base, unsigned j) {
+  if constexpr (!DROP) return 1.f;
+  return (mix32((row_base + j) ^ key) >> 8) >= thresh ? scale : 0.f;
 }
 
 // padded (h, Rh+4, Rw+4) copy of the table / accumulation of the padded gradient back into (h, Rh, Rw)
@@ -219,7 +241,7 @@ __device__ __forceinline__ void axpyR(float2 (*acc)[DH / 2], const float* a, con
   }
 }
 
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(TQ / RQ, FWD_MINB) rpe_attn_fwd_kernel(const __grid_constant__ RpeArgs a) {
   constexpr int R = RQ, NT = TQ / R;
   __shared__ __align__(16) float sK[TK * PAD];
@@ -249,6 +271,7 @@ __global__ void __launch_bounds__(TQ / RQ, FWD_MINB) rpe_attn_fwd_kernel(const _
     qy[r] = rpe_query_half(grid_coord(iy, a.Hq), a.Rh); qx[r] = rpe_query_half(grid_coord(ixq, a.Wq), a.Rw);
     m[r] = -INFINITY; l[r] = 0.f;
   }
+  const unsigned dkey = drop_key(a.seed_lo, a.seed_hi, bh);
   const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
 
   for (int j0 = jbeg; j0 < jend; j0 += TK) {
@@ -291,7 +314,8 @@ __global__ void __launch_bounds__(TQ / RQ, FWD_MINB) rpe_attn_fwd_kernel(const _
 #pragma unroll
         for (int jj = 0; jj < CH; ++jj) {
           s[r][jj] = __expf(s[r][jj] - mn);
-          l[r] += s[r][jj];
+          l[r] += s[r][jj];                                   // the softmax denominator is taken before the dropout
+          s[r][jj] *= drop_mul<DROP>(a.drop_thresh, a.drop_scale, dkey, (unsigned)iq[r] * (unsigned)a.Ns, (unsigned)(j0 + jc + jj));
         }
         m[r] = mn;
       }
@@ -405,7 +429,7 @@ __device__ __forceinline__ void stage_async(float* __restrict__ dst, const float
 }
 __device__ __forceinline__ void stage_async_wait() { asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory"); }
 
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(const __grid_constant__ RpeArgs a) {
   constexpr int KS = DH / 8;                 // k-steps of S = Q^T K (channels) = n-tiles of O (channels)
   constexpr int NT = CHM / 8;                // key n-tiles per softmax step = k-steps of O += P V
@@ -442,6 +466,8 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
   for (int nv = 0; nv < KS; ++nv)
 #pragma unroll
     for (int e = 0; e < 4; ++e) o[nv][e] = 0.f;
+  const unsigned dkey = drop_key(a.seed_lo, a.seed_hi, bh);
+  const unsigned rowb[2] = {(unsigned)iq[0] * (unsigned)a.Ns, (unsigned)iq[1] * (unsigned)a.Ns};
 
   const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
   for (int j0 = jbeg; j0 < jend; j0 += TK) {
@@ -515,6 +541,7 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
         for (int e = 0; e < 4; ++e) {
           sc[nt][e] = __expf(sc[nt][e] - m[e >> 1]);
           l[e >> 1] += sc[nt][e];                  // per-lane partial row sum, reduced over the quad at the end
+          sc[nt][e] *= drop_mul<DROP>(a.drop_thresh, a.drop_scale, dkey, rowb[e >> 1], (unsigned)(j0 + jc + nt * 8 + 2 * t + (e & 1)));
         }
       // ---- O += P V; k-step kt = the probabilities of key tile kt, operand columns (t, t+4) = keys (2t, 2t+1)
 #pragma unroll
@@ -614,7 +641,7 @@ __global__ void __launch_bounds__(256) rpe_delta_kernel(const __grid_constant__ 
 }
 
 // dQ: thread = query row, streams K/V tiles
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const __grid_constant__ RpeArgs a) {
   __shared__ __align__(16) float sK[TK * PAD];
   __shared__ __align__(16) float sV[TK * PAD];
@@ -639,6 +666,7 @@ __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const _
   const float delta = live ? __ldg(a.delta + (size_t)bh * a.Nq + i) : 0.f;
   const int iy = i / a.Wq, ixq = i - iy * a.Wq;
   const float qy = rpe_query_half(grid_coord(iy, a.Hq), a.Rh), qx = rpe_query_half(grid_coord(ixq, a.Wq), a.Rw);
+  const unsigned dkey = drop_key(a.seed_lo, a.seed_hi, bh), rowb = (unsigned)i * (unsigned)a.Ns;
 
   const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
   for (int j0 = jbeg; j0 < jend; j0 += TK) {
@@ -658,7 +686,7 @@ __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const _
       float tv[4];
       const float s = dot32<DH>(qr, sK + jj * PAD) + rpe_bias(table, b, a.Wp, tv);
       const float pr = __expf(s - lse);
-      const float dp = dot32<DH>(go, sV + jj * PAD);
+      const float dp = dot32<DH>(go, sV + jj * PAD) * drop_mul<DROP>(a.drop_thresh, a.drop_scale, dkey, rowb, (unsigned)(j0 + jj));
       axpy32<DH>(dq, pr * (dp - delta), sK + jj * PAD);
     }
   }
@@ -681,7 +709,7 @@ __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const _
 #ifndef K3_DQ_MMA_MINB
 #define K3_DQ_MMA_MINB 3
 #endif
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kernel(const __grid_constant__ RpeArgs a) {
   constexpr int KS = DH / 8, NT = CHM / 8;
   __shared__ __align__(16) float sKh[TK * PAD], sKl[TK * PAD], sVh[TK * PAD], sVl[TK * PAD];
@@ -722,6 +750,8 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
   for (int nv = 0; nv < KS; ++nv)
 #pragma unroll
     for (int e = 0; e < 4; ++e) dq[nv][e] = 0.f;
+  const unsigned dkey = drop_key(a.seed_lo, a.seed_hi, bh);
+  const unsigned rowb[2] = {(unsigned)iq[0] * (unsigned)a.Ns, (unsigned)iq[1] * (unsigned)a.Ns};
 
   const int jbeg = blockIdx.z * a.tiles_per_split * TK, jend = min(a.Ns, jbeg + a.tiles_per_split * TK);
   for (int j0 = jbeg; j0 < jend; j0 += TK) {
@@ -783,7 +813,8 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
           const Bilin b = rpe_taps(ay[r], ax[r], kk ? pp.z : pp.x, kk ? pp.w : pp.y, a.Rh, a.Rw, a.Wp);
           float tv[4];
           const float pr = __expf(sc[nt][e] + rpe_bias(table, b, a.Wp, tv) - lse[r]);
-          sc[nt][e] = (j0 + jc + nt * 8 + 2 * t + kk < a.Ns) ? pr * (dp[nt][e] - delta[r]) : 0.f;
+          const float dm = drop_mul<DROP>(a.drop_thresh, a.drop_scale, dkey, rowb[r], (unsigned)(j0 + jc + nt * 8 + 2 * t + kk));
+          sc[nt][e] = (j0 + jc + nt * 8 + 2 * t + kk < a.Ns) ? pr * (dm * dp[nt][e] - delta[r]) : 0.f;
         }
       }
       // dQ += dS K; operand columns (t, t+4) = keys (2t, 2t+1)
@@ -848,7 +879,7 @@ constexpr int TKB = 128, TQB = K3_TQB;
 constexpr int CS = K3_CS;
 constexpr int DKV_MINB = CS == 1 ? K3_DKV_MINB : K3_DKV_MINB2;
 
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(TKB * CS, DKV_MINB) rpe_attn_bwd_dkv_kernel(const __grid_constant__ RpeArgs a) {
   constexpr int DL = DH / CS;         // channels per lane
   __shared__ __align__(16) float sQ[TQB * PAD];
@@ -881,6 +912,7 @@ __global__ void __launch_bounds__(TKB * CS, DKV_MINB) rpe_attn_bwd_dkv_kernel(co
   pj = make_float2(rpe_key_half(pj.x, a.Rh), rpe_key_half(pj.y, a.Rw));
   float giy = 0.f, gix = 0.f;
   const bool want_bias_grad = (a.grad_rpe_pad != nullptr) || (a.grad_pos != nullptr);
+  const unsigned dkey = drop_key(a.seed_lo, a.seed_hi, bh);
 
   const int ibeg = blockIdx.z * a.tiles_per_split * TQB, iend = min(a.Nq, ibeg + a.tiles_per_split * TQB);
   for (int i0 = ibeg; i0 < iend; i0 += TQB) {
@@ -915,8 +947,9 @@ __global__ void __launch_bounds__(TKB * CS, DKV_MINB) rpe_attn_bwd_dkv_kernel(co
       }
       const float s = qk + rpe_bias(table, b, a.Wp, tv);
       const float pr = __expf(s - r.z);
-      axpy32<DL>(dv, pr, sG + ii * PAD + c0);
-      const float ds = pr * (dp - r.w);
+      const float dm = drop_mul<DROP>(a.drop_thresh, a.drop_scale, dkey, (unsigned)(i0 + ii) * (unsigned)a.Ns, (unsigned)j);
+      axpy32<DL>(dv, pr * dm, sG + ii * PAD + c0);
+      const float ds = pr * (dm * dp - r.w);
       axpy32<DL>(dk, ds, sQ + ii * PAD + c0);
       if (want_bias_grad) {
         gix = fmaf(ds, b.wy0 * (tv[1] - tv[0]) + b.wy1 * (tv[3] - tv[2]), gix);
@@ -965,7 +998,7 @@ __global__ void __launch_bounds__(TKB * CS, DKV_MINB) rpe_attn_bwd_dkv_kernel(co
 #endif
 constexpr int TKM = 64;                      // keys per CTA (4 warps x 16)
 
-template <int DH>
+template <int DH, bool DROP>
 __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_kernel(const __grid_constant__ RpeArgs a) {
   constexpr int KS = DH / 8, NT = CHM / 8;
   __shared__ __align__(16) float sQh[TK * PAD], sQl[TK * PAD], sGh[TK * PAD], sGl[TK * PAD];
@@ -1005,6 +1038,7 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
   for (int nv = 0; nv < KS; ++nv)
 #pragma unroll
     for (int e = 0; e < 4; ++e) { dk[nv][e] = 0.f; dv[nv][e] = 0.f; }
+  const unsigned dkey = drop_key(a.seed_lo, a.seed_hi, bh);
 
   const int ibeg = blockIdx.z * a.tiles_per_split * TK, iend = min(a.Nq, ibeg + a.tiles_per_split * TK);
   for (int i0 = ibeg; i0 < iend; i0 += TK) {
@@ -1075,8 +1109,9 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
           const bool ok = (i0 + jc + nt * 8 + 2 * t + kk < a.Nq) && (jk[r] < a.Ns);
           const float bias = rpe_bias(table, b, a.Wp, tv);          // always sampled: the taps feed the gradients below
           const float pr = ok ? __expf(sc[nt][e] + bias - rq.z) : 0.f;
-          const float ds = pr * (dp[nt][e] - rq.w);
-          sc[nt][e] = pr;
+          const float dm = drop_mul<DROP>(a.drop_thresh, a.drop_scale, dkey, (unsigned)(i0 + jc + nt * 8 + 2 * t + kk) * (unsigned)a.Ns, (unsigned)jk[r]);
+          const float ds = pr * (dm * dp[nt][e] - rq.w);
+          sc[nt][e] = pr * dm;
           dp[nt][e] = ds;
           if (want_bias_grad) {
             gix[r] = fmaf(ds, b.wy0 * (tv[1] - tv[0]) + b.wy1 * (tv[3] - tv[2]), gix[r]);
@@ -1250,12 +1285,34 @@ static float* presplit_kv(RpeArgs& a, const float* k, const float* v, float* bas
   return base + 4 * n;
 }
 
-extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
+// launch KERN<Dh, dropout?> (Dh = 32 or 16)
+#define K3_LAUNCH(KERN, GRID, BLOCK)                                   \
+  do {                                                                 \
+    if (Dh == 32) {                                                    \
+      if (a.drop_thresh) KERN<32, true><<<GRID, BLOCK, 0, st>>>(a);    \
+      else KERN<32, false><<<GRID, BLOCK, 0, st>>>(a);                 \
+    } else {                                                           \
+      if (a.drop_thresh) KERN<16, true><<<GRID, BLOCK, 0, st>>>(a);    \
+      else KERN<16, false><<<GRID, BLOCK, 0, st>>>(a);                 \
+    }                                                                  \
+  } while (0)
+
+static int set_dropout(RpeArgs& a, float drop_p, unsigned long long seed) {
+  BEVR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "rpe_attn: drop_p must be in [0, 1) (got %g)", (double)drop_p);
+  a.drop_thresh = (unsigned)(drop_p * 16777216.0f);       // p < 2^-24 rounds to "no dropout"
+  a.drop_scale = 1.f / (1.f - drop_p);
+  a.seed_lo = (unsigned)(seed & 0xffffffffull); a.seed_hi = (unsigned)(seed >> 32);
+  return 0;
+}
+
+static int rpe_fwd_impl(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
                                  float* out, float* lse, void* workspace, int BH, int h, int hpg, int Dh, int Hq,
-                                 int Wq, int Ns, int Rh, int Rw, float scale, int flags, void* stream) {
+                                 int Wq, int Ns, int Rh, int Rw, float scale, int flags, float drop_p,
+                                 unsigned long long seed, void* stream) {
   if (int rc = validate(BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw)) return rc;
   BEVR_REQUIRE(q && k && v && rpe && pos && out && lse && workspace, "rpe_attn_fwd: NULL pointer argument");
   RpeArgs a = {};
+  if (int rc = set_dropout(a, drop_p, seed)) return rc;
   a.q = q; a.k = k; a.v = v; a.rpe_pad = (const float*)workspace; a.pos = pos; a.o_out = out; a.o_lse = lse;
   a.BH = BH; a.h = h; a.hpg = hpg; a.Hq = Hq; a.Wq = Wq; a.Nq = Hq * Wq; a.Ns = Ns; a.Rh = Rh; a.Rw = Rw;
   a.Hp = Rh + 4; a.Wp = Rw + 4;
@@ -1274,12 +1331,10 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   }
   if (mma) {
     dim3 grid((a.Nq + TQM - 1) / TQM, BH, a.split);
-    if (Dh == 32) rpe_attn_fwd_mma_kernel<32><<<grid, 128, 0, st>>>(a);
-    else rpe_attn_fwd_mma_kernel<16><<<grid, 128, 0, st>>>(a);
+    K3_LAUNCH(rpe_attn_fwd_mma_kernel, grid, 128);
   } else {
     dim3 grid((a.Nq + TQ - 1) / TQ, BH, a.split);
-    if (Dh == 32) rpe_attn_fwd_kernel<32><<<grid, TQ / RQ, 0, st>>>(a);
-    else rpe_attn_fwd_kernel<16><<<grid, TQ / RQ, 0, st>>>(a);
+    K3_LAUNCH(rpe_attn_fwd_kernel, grid, TQ / RQ);
   }
   if (int rc = check_launch("rpe_attn_fwd")) return rc;
   if (a.split > 1) {
@@ -1291,15 +1346,28 @@ extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v,
   return 0;
 }
 
-extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
+extern "C" int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
+                                 float* out, float* lse, void* workspace, int BH, int h, int hpg, int Dh, int Hq,
+                                 int Wq, int Ns, int Rh, int Rw, float scale, int flags, void* stream) {
+  return rpe_fwd_impl(q, k, v, rpe, pos, out, lse, workspace, BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, scale, flags, 0.f, 0ull, stream);
+}
+extern "C" int bevr_rpe_attn_fwd_dropout(const float* q, const float* k, const float* v, const float* rpe,
+                                         const float* pos, float* out, float* lse, void* workspace, int BH, int h,
+                                         int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw, float scale, int flags,
+                                         float drop_p, unsigned long long seed, void* stream) {
+  return rpe_fwd_impl(q, k, v, rpe, pos, out, lse, workspace, BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, scale, flags, drop_p, seed, stream);
+}
+
+static int rpe_bwd_impl(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
                                  const float* out, const float* lse, const float* grad_out, float* grad_q,
                                  float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos, float* delta_ws,
                                  void* workspace, int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns, int Rh,
-                                 int Rw, float scale, int flags, void* stream) {
+                                 int Rw, float scale, int flags, float drop_p, unsigned long long seed, void* stream) {
   if (int rc = validate(BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw)) return rc;
   BEVR_REQUIRE(q && k && v && rpe && pos && out && lse && grad_out && delta_ws && workspace,
                "rpe_attn_bwd: NULL pointer argument");
   RpeArgs a = {};
+  if (int rc = set_dropout(a, drop_p, seed)) return rc;
   float* pad = (float*)workspace;
   float* gpad = pad + pad_floats(h, Rh, Rw);
   a.q = q; a.k = k; a.v = v; a.rpe_pad = pad; a.pos = pos; a.out = out; a.lse = lse; a.grad_out = grad_out;
@@ -1339,13 +1407,8 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
     a.split = pick_split((long long)nqt * BH, mma_dq ? K3_DQ_MMA_MINB : K3_DQ_MINB, (Ns + TK - 1) / TK, &a.tiles_per_split);
     if (a.split > 1)
       if (int rc = check_cuda(cudaMemsetAsync(grad_q, 0, (size_t)BH * Dh * a.Nq * sizeof(float), st), "rpe_attn_bwd zero-fill")) return rc;
-    if (mma_dq) {
-      if (Dh == 32) rpe_attn_bwd_dq_mma_kernel<32><<<dim3(nqt, BH, a.split), 128, 0, st>>>(a);
-      else rpe_attn_bwd_dq_mma_kernel<16><<<dim3(nqt, BH, a.split), 128, 0, st>>>(a);
-    } else {
-      if (Dh == 32) rpe_attn_bwd_dq_kernel<32><<<dim3(nqt, BH, a.split), TQ, 0, st>>>(a);
-      else rpe_attn_bwd_dq_kernel<16><<<dim3(nqt, BH, a.split), TQ, 0, st>>>(a);
-    }
+    if (mma_dq) K3_LAUNCH(rpe_attn_bwd_dq_mma_kernel, dim3(nqt, BH, a.split), 128);
+    else K3_LAUNCH(rpe_attn_bwd_dq_kernel, dim3(nqt, BH, a.split), TQ);
     if (int rc = check_launch("rpe_attn_bwd dq")) return rc;
   }
   if (grad_k || grad_v || grad_rpe || grad_pos) {
@@ -1359,13 +1422,8 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
       if (grad_v)
         if (int rc = check_cuda(cudaMemsetAsync(grad_v, 0, (size_t)BH * Dh * Ns * sizeof(float), st), "rpe_attn_bwd zero-fill")) return rc;
     }
-    if (mma_dkv) {
-      if (Dh == 32) rpe_attn_bwd_dkv_mma_kernel<32><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a);
-      else rpe_attn_bwd_dkv_mma_kernel<16><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a);
-    } else {
-      if (Dh == 32) rpe_attn_bwd_dkv_kernel<32><<<dim3(nkt, BH, a.split), TKB * CS, 0, st>>>(a);
-      else rpe_attn_bwd_dkv_kernel<16><<<dim3(nkt, BH, a.split), TKB * CS, 0, st>>>(a);
-    }
+    if (mma_dkv) K3_LAUNCH(rpe_attn_bwd_dkv_mma_kernel, dim3(nkt, BH, a.split), 128);
+    else K3_LAUNCH(rpe_attn_bwd_dkv_kernel, dim3(nkt, BH, a.split), TKB * CS);
     if (int rc = check_launch("rpe_attn_bwd dkv")) return rc;
   }
   if (grad_rpe) {
@@ -1373,4 +1431,22 @@ extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v,
     if (int rc = check_launch("rpe_attn_bwd unpad")) return rc;
   }
   return 0;
+}
+
+extern "C" int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v, const float* rpe, const float* pos,
+                                 const float* out, const float* lse, const float* grad_out, float* grad_q,
+                                 float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos, float* delta_ws,
+                                 void* workspace, int BH, int h, int hpg, int Dh, int Hq, int Wq, int Ns, int Rh,
+                                 int Rw, float scale, int flags, void* stream) {
+  return rpe_bwd_impl(q, k, v, rpe, pos, out, lse, grad_out, grad_q, grad_k, grad_v, grad_rpe, grad_pos, delta_ws, workspace,
+                      BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, scale, flags, 0.f, 0ull, stream);
+}
+extern "C" int bevr_rpe_attn_bwd_dropout(const float* q, const float* k, const float* v, const float* rpe,
+                                         const float* pos, const float* out, const float* lse, const float* grad_out,
+                                         float* grad_q, float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos,
+                                         float* delta_ws, void* workspace, int BH, int h, int hpg, int Dh, int Hq, int Wq,
+                                         int Ns, int Rh, int Rw, float scale, int flags, float drop_p,
+                                         unsigned long long seed, void* stream) {
+  return rpe_bwd_impl(q, k, v, rpe, pos, out, lse, grad_out, grad_q, grad_k, grad_v, grad_rpe, grad_pos, delta_ws, workspace,
+                      BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, scale, flags, drop_p, seed, stream);
 }

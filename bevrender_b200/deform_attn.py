@@ -10,8 +10,9 @@ attention with sampled relative-position bias (K3) run as sm_100a kernels behind
 
 Differences from the reference, all deliberate:
   * nothing of size (Nq, Ns) is materialised (the reference needs 51 GB/sample at 200x200);
-  * attention dropout inside the fused kernel is not implemented: ``attn_drop_rate > 0`` raises in
-    training mode (the reference default is 0.0);
+  * attention dropout (``attn_drop_rate``, reference default 0.0) is fused into K3: same Bernoulli(1 - p) / rescale
+    semantics as ``nn.Dropout`` on the softmax matrix, but the keep mask comes from a counter-based hash seeded from
+    torch's default generator, not from torch's Philox stream over the (never materialised) attention matrix;
   * ``TSADeformableAttention`` with ``n_groups > 1`` works here (the reference raises at
     TSA_deform_attn.py:278-283); ``SCADeformableAttention`` with ``n_views > 1`` raises here exactly
     as the reference does (SCA_deform_attn.py:248-255), with a clearer message.
@@ -110,8 +111,6 @@ class _DeformAttnBase(nn.Module):
 
     def _attend(self, x_grouped, pos, query):
         """gather (K1/K2) -> K/V projections -> fused RPE attention (K3) -> (B, C, Hq, Wq)."""
-        if self.training and self.attn_drop_rate.p > 0:
-            raise NotImplementedError("attention dropout is not fused into the sm_100a kernel; use attn_drop_rate=0")
         B, C, Hq, Wq = query.shape
         Ns = pos.shape[1] * pos.shape[2]
         xs = grid_gather(x_grouped, pos).reshape(B, C, Ns)
@@ -120,7 +119,10 @@ class _DeformAttnBase(nn.Module):
         k = self._pointwise(self.proj_k, xs).reshape(B * self.n_heads, self.n_channel_per_head, Ns)
         v = self._pointwise(self.proj_v, xs).reshape(B * self.n_heads, self.n_channel_per_head, Ns)
         q = query.reshape(B * self.n_heads, self.n_channel_per_head, Hq * Wq)
-        out = rpe_attention(q, k, v, self.rpe_table, pos.reshape(-1, Ns, 2), Hq, Wq, self.n_groups, self.scale)
+        # attention dropout (attn_drop_rate, TSA_deform_attn.py:313-323 / SCA_deform_attn.py:402-410) is fused into K3
+        drop = float(self.attn_drop_rate.p) if self.training else 0.0
+        out = rpe_attention(q, k, v, self.rpe_table, pos.reshape(-1, Ns, 2), Hq, Wq, self.n_groups, self.scale,
+                            dropout_p=drop)
         return out.reshape(B, C, Hq, Wq)
 
 

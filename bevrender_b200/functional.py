@@ -140,7 +140,7 @@ def project_points(points, cam_T, K, img_w, img_h):
 
 class _RpeAttention(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, q, k, v, rpe, pos, Hq, Wq, hpg, scale, flags):
+    def forward(ctx, q, k, v, rpe, pos, Hq, Wq, hpg, scale, flags, drop_p, seed):
         _need_cuda(q, k, v, rpe, pos)
         q, k, v = q.contiguous().float(), k.contiguous().float(), v.contiguous().float()
         rpe, pos = rpe.contiguous().float(), pos.contiguous().float()
@@ -150,17 +150,18 @@ class _RpeAttention(torch.autograd.Function):
         out = torch.empty_like(q)
         lse = torch.empty(BH, Nq, dtype=torch.float32, device=q.device)
         ws = torch.empty(_lib.lib().bevr_rpe_attn_workspace_bytes(BH, h, Dh, Nq, Ns, Rh, Rw, 0), dtype=torch.uint8, device=q.device)
-        _lib.check(_lib.lib().bevr_rpe_attn_fwd(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
-                                                _ptr(ws), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, float(scale), flags, _stream()),
+        _lib.check(_lib.lib().bevr_rpe_attn_fwd_dropout(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
+                                                        _ptr(ws), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, float(scale), flags,
+                                                        float(drop_p), int(seed), _stream()),
                    "bevr_rpe_attn_fwd")
         ctx.save_for_backward(q, k, v, rpe, pos, out, lse)
-        ctx.meta = (Hq, Wq, hpg, float(scale), flags)
+        ctx.meta = (Hq, Wq, hpg, float(scale), flags, float(drop_p), int(seed))
         return out
 
     @staticmethod
     def backward(ctx, grad_out):
         q, k, v, rpe, pos, out, lse = ctx.saved_tensors
-        Hq, Wq, hpg, scale, flags = ctx.meta
+        Hq, Wq, hpg, scale, flags, drop_p, seed = ctx.meta
         BH, Dh, Nq = q.shape
         Ns = k.shape[2]
         h, Rh, Rw = rpe.shape
@@ -173,28 +174,37 @@ class _RpeAttention(torch.autograd.Function):
         gp = torch.zeros_like(pos) if need[4] else None
         delta = torch.empty_like(lse)
         ws = torch.empty(_lib.lib().bevr_rpe_attn_workspace_bytes(BH, h, Dh, Nq, Ns, Rh, Rw, 1), dtype=torch.uint8, device=q.device)
-        _lib.check(_lib.lib().bevr_rpe_attn_bwd(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
-                                                _ptr(grad_out), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(gr), _ptr(gp),
-                                                _ptr(delta), _ptr(ws), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, scale,
-                                                flags, _stream()),
+        _lib.check(_lib.lib().bevr_rpe_attn_bwd_dropout(_ptr(q), _ptr(k), _ptr(v), _ptr(rpe), _ptr(pos), _ptr(out), _ptr(lse),
+                                                        _ptr(grad_out), _ptr(gq), _ptr(gk), _ptr(gv), _ptr(gr), _ptr(gp),
+                                                        _ptr(delta), _ptr(ws), BH, h, hpg, Dh, Hq, Wq, Ns, Rh, Rw, scale,
+                                                        flags, drop_p, seed, _stream()),
                    "bevr_rpe_attn_bwd")
-        return gq, gk, gv, gr, gp, None, None, None, None, None
+        return gq, gk, gv, gr, gp, None, None, None, None, None, None, None
 
 
 K3_AUTO, K3_FFMA, K3_MMA = 0, 1, 2
 
 
-def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None, family=K3_AUTO):
+def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None, family=K3_AUTO, dropout_p=0.0, seed=None):
     """K3: softmax_j(q.k*scale + bilinear(rpe_table[head], (qgrid_i - pos_j)/2)) . v, never materialised.
 
     q (B*h, Dh, Hq*Wq); k, v (B*h, Dh, Ns); rpe_table (h, Rh, Rw); pos (B*g, Ns, 2) in (y, x);
     returns (B*h, Dh, Hq*Wq).  Replaces TSA_deform_attn.py:245-330 / SCA_deform_attn.py:331-411.
     ``family``: K3_AUTO picks the kernel family by problem size; K3_FFMA / K3_MMA force one (tests, benchmarks).
+    ``dropout_p`` > 0: attention dropout fused into the kernels (nn.Dropout on the softmax matrix,
+    TSA_deform_attn.py:313-323); the keep mask is a hash of (``seed``, head, query, key) regenerated in backward.
+    ``seed`` None draws one from torch's default generator (so ``torch.manual_seed`` makes a run reproducible).
     """
     h = rpe_table.shape[0]
     if scale is None:
         scale = q.shape[1] ** -0.5
-    return _RpeAttention.apply(q, k, v, rpe_table, pos, int(Hq), int(Wq), h // n_groups, scale, int(family))
+    dropout_p = float(dropout_p)
+    if not 0.0 <= dropout_p < 1.0:
+        raise ValueError(f"rpe_attention: dropout_p must be in [0, 1), got {dropout_p}")
+    if dropout_p > 0.0 and seed is None:
+        seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
+    return _RpeAttention.apply(q, k, v, rpe_table, pos, int(Hq), int(Wq), h // n_groups, scale, int(family),
+                               dropout_p, int(seed or 0))
 
 
 class _OffsetHead(torch.autograd.Function):

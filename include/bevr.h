@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define BEVR_VERSION 200
+#define BEVR_VERSION 210
 
 enum { BEVR_F32 = 0, BEVR_BF16 = 1 };
 
@@ -146,6 +146,25 @@ int bevr_rpe_attn_bwd(const float* q, const float* k, const float* v, const floa
                       float* grad_q, float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos,
                       float* delta_ws, void* workspace, int BH, int h, int hpg, int Dh, int Hq,
                       int Wq, int Ns, int Rh, int Rw, float scale, int flags, void* stream);
+
+/* K3 with attention dropout (nn.Dropout on the softmax matrix, TSA_deform_attn.py:313-323, SCA_deform_attn.py:402-410):
+ * every probability is kept with probability 1 - drop_p and scaled by 1 / (1 - drop_p) before it multiplies v; the
+ * softmax denominator (and `lse`) are those of the undropped attention.  The keep mask is a counter-based hash of
+ * (seed, b*h, query, key) -- never stored; the backward regenerates it from the same `drop_p` and `seed` the forward got.
+ * Same distribution as torch's dropout, a different random stream (the reference draws from torch's Philox generator over
+ * a matrix that does not exist here); oracle/deform_attn.py::dropout_keep restates the hash.  drop_p in [0, 1); 0 is the
+ * plain entry point above.
+ */
+int bevr_rpe_attn_fwd_dropout(const float* q, const float* k, const float* v, const float* rpe,
+                              const float* pos, float* out, float* lse, void* workspace, int BH, int h,
+                              int hpg, int Dh, int Hq, int Wq, int Ns, int Rh, int Rw, float scale,
+                              int flags, float drop_p, unsigned long long seed, void* stream);
+int bevr_rpe_attn_bwd_dropout(const float* q, const float* k, const float* v, const float* rpe,
+                              const float* pos, const float* out, const float* lse, const float* grad_out,
+                              float* grad_q, float* grad_k, float* grad_v, float* grad_rpe, float* grad_pos,
+                              float* delta_ws, void* workspace, int BH, int h, int hpg, int Dh, int Hq,
+                              int Wq, int Ns, int Rh, int Rw, float scale, int flags, float drop_p,
+                              unsigned long long seed, void* stream);
 
 /* ---------------------------------------------------------------------------
  * K5  rotation-sweep correlation of a BEV template against an aerial-map tile (tcgen05 tensor cores).

@@ -68,12 +68,40 @@ def rpe_bias_dense(rpe_table, pos, Hq, Wq, n_groups):
     return bias.reshape(Bg * n, Hq * Wq, Ns)
 
 
-def rpe_attention_dense(q, k, v, rpe_table, pos, Hq, Wq, n_groups, scale):
+def _mix32(x):
+    import numpy as np
+    x = x.astype(np.uint32)
+    x ^= x >> np.uint32(16); x *= np.uint32(0x85ebca6b); x ^= x >> np.uint32(13); x *= np.uint32(0xc2b2ae35)
+    x ^= x >> np.uint32(16)
+    return x
+
+
+def dropout_keep(seed, BH, Nq, Ns, p):
+    """Keep mask (BH, Nq, Ns) bool of K3's fused attention dropout: restatement of the counter-based hash of
+    csrc/rpe_attn.cu (``drop_key`` / ``drop_mul``).  The reference applies nn.Dropout(attn_drop_rate) to the softmax
+    matrix (TSA_deform_attn.py:313-323, SCA_deform_attn.py:402-410), i.e. torch's own Philox stream over a matrix K3
+    never forms: that stream cannot be reproduced, so for p > 0 parity means "same result as the dense reference math
+    under THIS mask" plus the keep rate -- parity unpinned vs reference for the random stream itself."""
+    import numpy as np
+    with np.errstate(over="ignore"):
+        lo, hi = np.uint32(seed & 0xffffffff), np.uint32(seed >> 32)
+        bh = np.arange(BH, dtype=np.uint32)
+        key = _mix32(lo + bh * np.uint32(0x9e3779b9)) ^ hi                       # (BH,)
+        idx = (np.arange(Nq, dtype=np.uint32)[:, None] * np.uint32(Ns) + np.arange(Ns, dtype=np.uint32)[None, :])
+        x = _mix32(idx[None] ^ key[:, None, None])
+    thresh = np.uint32(np.float32(p) * np.float32(16777216.0))
+    return torch.from_numpy((x >> np.uint32(8)) >= thresh)
+
+
+def rpe_attention_dense(q, k, v, rpe_table, pos, Hq, Wq, n_groups, scale, drop_p=0.0, drop_keep=None):
     """softmax_j(q.k*scale + bias) . v ; q (B*h,Dh,Nq), k/v (B*h,Dh,Ns) -> (B*h,Dh,Nq).
-    TSA_deform_attn.py:245-330, SCA_deform_attn.py:331-411."""
+    TSA_deform_attn.py:245-330, SCA_deform_attn.py:331-411.  ``drop_keep`` (B*h, Nq, Ns) bool: the attention dropout
+    of TSA_deform_attn.py:313-323 with an explicit keep mask (kept probabilities scaled by 1 / (1 - drop_p))."""
     attn = torch.einsum("bcm,bcn->bmn", q, k).mul(scale)
     attn = attn + rpe_bias_dense(rpe_table, pos, Hq, Wq, n_groups)
     attn = F.softmax(attn, dim=2)
+    if drop_keep is not None:
+        attn = attn * drop_keep.to(attn) * (1.0 / (1.0 - float(torch.tensor(drop_p, dtype=torch.float32))))
     return torch.einsum("bmn,bcn->bcm", attn, v)
 
 

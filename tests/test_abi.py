@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     for s in header_symbols():
         assert hasattr(handle, s), f"libbevr.so lacks {s}"
     assert set(header_symbols()) == set(_lib.SIGNATURES), "ctypes table and header disagree"
-    assert _lib.lib().bevr_version() == _lib.EXPECTED_VERSION == 200
+    assert _lib.lib().bevr_version() == _lib.EXPECTED_VERSION == 210
 
 
 def test_argument_validation_returns_negative_and_message():

@@ -119,3 +119,14 @@ def test_projection_oracle_gray_mask_bit_exact():
     assert np.array_equal(mask.numpy(), g["mask"])
     assert np.array_equal(uv.numpy().view(np.uint32), g["uv"].view(np.uint32))
     assert int(plain.sum()) > int(mask.sum()) > 0          # the gray band really removes points
+
+
+def test_dropout_keep_mask_is_a_fair_coin_per_head_and_seed():
+    """oracle.dropout_keep (the restatement of K3's dropout hash): keep rate 1 - p, different per head and per seed,
+    deterministic in the seed."""
+    from oracle import deform_attn as oda
+    a = oda.dropout_keep(7, 4, 50, 60, 0.25)
+    assert a.shape == (4, 50, 60) and abs(a.float().mean().item() - 0.75) < 0.02
+    assert torch.equal(a, oda.dropout_keep(7, 4, 50, 60, 0.25))
+    assert not torch.equal(a[0], a[1]) and not torch.equal(a, oda.dropout_keep(8, 4, 50, 60, 0.25))
+    assert oda.dropout_keep(7, 1, 8, 8, 0.0).all()

@@ -126,3 +126,55 @@ def test_rpe_attention_n100_backward_vs_dense_oracle_on_device():
             assert_close(a.grad, b.grad, FP32_TOL, "grad_" + name)
     finally:
         torch.backends.cuda.matmul.allow_tf32 = old
+
+
+@pytest.mark.parametrize("B,h,g,Hq,Wq,Hk,Wk,mul,spread,p", [
+    (2, 2, 1, 14, 14, 14, 14, 1, 0.05, 0.1),    # TSA
+    (1, 2, 1, 14, 14, 7, 70, 5, 0.3, 0.25),     # SCA shape
+    (1, 2, 2, 50, 50, 10, 13, 1, 0.1, 0.5),     # ragged row tile, work split over key ranges
+])
+def test_attention_dropout_matches_dense_oracle_under_the_same_mask(B, h, g, Hq, Wq, Hk, Wk, mul, spread, p):
+    """attn_drop_rate > 0 (TSA_deform_attn.py:313-323): output and all five gradients against the dense reference math
+    with the keep mask of the kernels' hash (the backward kernels regenerate it); the keep rate is 1 - p."""
+    import bevrender_b200 as bb
+    q, k, v, rpe, pos, go = _case(B, h, g, Hq, Wq, Hk, Wk, mul, 3, spread)
+    seed = 0x1234_5678_9abc_def1
+    keep = oda.dropout_keep(seed, B * h, Hq * Wq, Hk * Wk, p)
+    assert abs(keep.float().mean().item() - (1 - p)) < 0.01
+    cpu = [t.clone().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    ref = oda.rpe_attention_dense(*cpu, Hq, Wq, g, 32 ** -0.5, drop_p=p, drop_keep=keep)
+    ref.backward(go)
+    dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    out = bb.rpe_attention(*dev, Hq, Wq, g, family=FAMILY, dropout_p=p, seed=seed)
+    out.backward(go.cuda())
+    assert rel_err(out.cpu(), ref) < FP32_TOL
+    for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, cpu):
+        e = rel_err(a.grad.cpu(), b.grad)
+        assert e < FP32_TOL, f"grad_{name}: {e:.3e}"
+    # a different seed gives a different mask; p = 0 is the plain path bit for bit
+    out2 = bb.rpe_attention(*[t.detach() for t in dev], Hq, Wq, g, family=FAMILY, dropout_p=p, seed=seed + 1)
+    assert not torch.equal(out2, out.detach())
+    a0 = bb.rpe_attention(*[t.detach() for t in dev], Hq, Wq, g, family=FAMILY, dropout_p=0.0)
+    a1 = bb.rpe_attention(*[t.detach() for t in dev], Hq, Wq, g, family=FAMILY)
+    assert torch.equal(a0, a1)
+
+
+def test_module_attention_dropout_train_vs_eval():
+    """The drop-in modules accept attn_drop_rate > 0 like the reference's (TSA.py:30-44): active in training mode (seeded
+    from torch's generator, reproducible under torch.manual_seed), inactive in eval mode."""
+    import bevrender_b200 as bb
+    torch.manual_seed(0)
+    N, C = 14, 64
+    tsa = bb.TSADeformableAttention(N, C, 2, 1, 1, 3, True, 2, n_views=1, attn_drop_rate=0.2).cuda()
+    ref = bb.TSADeformableAttention(N, C, 2, 1, 1, 3, True, 2, n_views=1).cuda()
+    ref.load_state_dict(tsa.state_dict())
+    q, prev = torch.randn(2, C, N, N, device="cuda", requires_grad=True), torch.randn(2, C, N, N, device="cuda")
+    tsa.eval(); ref.eval()
+    assert torch.equal(tsa(prev, q, {}, True)[0], ref(prev, q, {}, True)[0])
+    tsa.train()
+    torch.manual_seed(5); a = tsa(prev, q, {}, True)[0]
+    torch.manual_seed(5); b = tsa(prev, q, {}, True)[0]
+    torch.manual_seed(6); c = tsa(prev, q, {}, True)[0]
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    a.sum().backward()
+    assert torch.isfinite(q.grad).all()
