@@ -329,9 +329,57 @@ def k3_leg():
             f().backward(go)
         t_fb = timeit_cuda(fb)
         pairs = BH * Nq * Ns
+        # algorithmic HBM bytes of the forward: q, out (BH, Dh, Nq); k, v (BH, Dh, Ns); pos; table -- the (Nq, Ns) matrix
+        # the reference materialises (pairs * 4 B, three times over) never exists
+        hbm_fwd = 4 * (2 * BH * Dh * Nq + 2 * BH * Dh * Ns + pos.numel() + rpe.numel())
         res[name] = {"fwd_ms": t_f, "bwd_ms": t_fb - t_f, "pairs": pairs, "fwd_pairs_per_s": pairs / (t_f * 1e-3),
-                     "fwd_bwd_pairs_per_s": pairs / (t_fb * 1e-3)}
+                     "fwd_bwd_pairs_per_s": pairs / (t_fb * 1e-3),
+                     "fwd_bilinear_gathers_per_s": pairs / (t_f * 1e-3), "fwd_table_tap_loads_per_s": 4 * pairs / (t_f * 1e-3),
+                     "fwd_hbm_bytes": hbm_fwd, "fwd_hbm_GBps": hbm_fwd / (t_f * 1e-3) / 1e9,
+                     "reference_attention_matrix_bytes": 4 * pairs,
+                     # executed tensor work: 2 contractions x 3 TF32 products x 2*Dh flops per pair, against the measured
+                     # legacy mma.sync TF32 rate of this chip (278 TFLOP/s, profiles/r1_exp_mma_sync.txt)
+                     "fwd_mma_TFLOPs": 2 * 3 * 2 * Dh * pairs / (t_f * 1e-3) / 1e12, "mma_sync_tf32_peak_TFLOPs": 278.0}
     res["shape"] = "N=56, C=64, 2 heads, B=8 (BH=16), Dh=32; TSA Ns=3136, SCA Ns=7840 (D=5)"
+    return res
+
+
+def config2_variants_leg():
+    """The other config-2 numbers SURVEY.md section 8(d) asks for beside the B=8 headline: B=1 (working set 430 MB, still
+    larger than L2) and the secondary camera-pyramid workload (value levels of a 512x640 image at /8../64, S=6800:
+    L2-resident), fp32, device-resident, fwd+bwd through the C ABI."""
+    from bevrender_b200 import _lib
+    from bevrender_b200.workloads import make_microbench_inputs
+    L = _lib.lib()
+    res = {}
+    for name, B, shp in (("b1", 1, None), ("camera_pyramid_b8", 8, [(64, 80), (32, 40), (16, 20), (8, 10)])):
+        d = make_microbench_inputs(B, seed=0, shapes=shp, device="cuda")
+        shapes, starts = d["spatial_shapes"], d["level_start_index"]
+        S, Nq = sum(h * w for h, w in shapes), N_SIDE * N_SIDE
+        out = torch.empty(B, Nq, HEADS * DH, device="cuda")
+        gv = torch.empty(B, S, HEADS, DH, device="cuda")
+        gl = torch.empty(B, Nq, HEADS, LEVELS, POINTS, 2, device="cuda")
+        gw = torch.empty(B, Nq, HEADS, LEVELS, POINTS, device="cuda")
+        hw = (C.c_int32 * (2 * LEVELS))(*[v for s_ in shapes for v in s_])
+        st = (C.c_int32 * LEVELS)(*starts)
+        P = lambda t: C.c_void_p(t.data_ptr())
+        cs = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def f():
+            _lib.check(L.bevr_msda_fwd(P(d["value"]), hw, st, P(d["sampling_locations"]), None, P(d["attention_weights"]),
+                                       P(out), B, S, HEADS, DH, Nq, LEVELS, POINTS, N_SIDE, 0, 0, cs), "msda_fwd")
+
+        def fb():
+            f()
+            _lib.check(L.bevr_msda_bwd(P(d["value"]), hw, st, P(d["sampling_locations"]), None, P(d["attention_weights"]),
+                                       P(d["grad_out"]), P(gv), P(gl), P(gw), None, B, S, HEADS, DH, Nq, LEVELS, POINTS,
+                                       N_SIDE, 0, 0, cs), "msda_bwd")
+        t_f, t_fb = timeit_cuda(f, 3, 20), timeit_cuda(fb, 3, 20)
+        nbytes = lambda *ts: sum(t.numel() * t.element_size() for t in ts)
+        ab = nbytes(d["value"], d["sampling_locations"], d["attention_weights"], out) + \
+            nbytes(d["grad_out"], d["value"], d["sampling_locations"], d["attention_weights"], gv, gl, gw)
+        res[name] = {"fwd_ms": t_f, "bwd_ms": t_fb - t_f, "queries_per_s": B * Nq / (t_fb * 1e-3),
+                     "algorithmic_GBps": ab / (t_fb * 1e-3) / 1e9, "levels": [list(s_) for s_ in shapes], "batch": B}
     return res
 
 
@@ -627,9 +675,10 @@ def main():
         except Exception as e:                       # never lose the contract line to the secondary legs
             train = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
     # ---- K3 / K5 alone and config 1 against the REAL reference on the host cores (single-GPU runs only)
-    k3 = k5 = config1 = None
+    k3 = k5 = config1 = config2v = None
     if rank == 0 and world == 1 and not args.no_extra:
-        for name, fn in (("k3", k3_leg), ("k5", k5_leg), ("config1", lambda: config1_leg(os.cpu_count() or 1))):
+        for name, fn in (("k3", k3_leg), ("k5", k5_leg), ("config1", lambda: config1_leg(os.cpu_count() or 1)),
+                         ("config2_variants", config2_variants_leg)):
             try:
                 r = fn()
             except Exception as e:
@@ -638,8 +687,10 @@ def main():
                 k3 = r
             elif name == "k5":
                 k5 = r
-            else:
+            elif name == "config1":
                 config1 = r
+            else:
+                config2v = r
 
     if rank == 0:
         # kernels of libbevr.so launched inside the timed device-resident region: msda_fwd + msda_bwd (sorted) per step,
@@ -651,7 +702,7 @@ def main():
                 "config": dict(workload_config(B, args.dtype), grad_value="fp32 main gradients (BEVR_GRAD_VALUE_F32)"
                                if bwd_flags else "storage dtype"), "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
                 "gpu_launches": args.steps * n_k, "train": train, "k3": k3, "k5": k5, "config1": config1,
-                "clocks": clk.summary()}
+                "config2_variants": config2v, "clocks": clk.summary()}
         emit(line)
     if world > 1:
         dist.destroy_process_group()

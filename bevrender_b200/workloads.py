@@ -3,12 +3,14 @@ import torch
 
 
 def make_microbench_inputs(B, seed=0, dtype=torch.float32, n_side=200, h=8, Dh=32, L=4, P=4,
-                           sigma_px=2.0, device="cpu"):
+                           sigma_px=2.0, device="cpu", shapes=None):
     """Synthetic inputs of BASELINE.json config 2:
     BEV pyramid [(N,N),(N/2,N/2),...], queries = cell centres of the NxN grid,
-    offsets ~ N(0,(2px)^2) per level, weights = softmax(N(0,1)) over L*P."""
+    offsets ~ N(0,(2px)^2) per level, weights = softmax(N(0,1)) over L*P.
+    ``shapes``: other value levels (the secondary workload of section 8d: the camera pyramid of a 512x640 image)."""
     g = torch.Generator().manual_seed(seed)
-    shapes = [(n_side >> l, n_side >> l) for l in range(L)]
+    shapes = [(n_side >> l, n_side >> l) for l in range(L)] if shapes is None else [tuple(s) for s in shapes]
+    L = len(shapes)
     starts, s = [], 0
     for H, W in shapes:
         starts.append(s)
