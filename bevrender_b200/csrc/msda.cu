@@ -505,7 +505,6 @@ template <typename T, int NV, int LPG, bool FAST>
 __global__ void __launch_bounds__(256, (NV == 8 ? MSDA_SORT_MINB8 : MSDA_SORT_MINB)) msda_bwd_sorted_kernel(const __grid_constant__ MsdaArgs a,
                                                                               const int maxbins) {
   constexpr unsigned VB = NV * sizeof(T);                // bytes of one lane's slice of a value row
-  constexpr int NG = 256 / LPG;                          // groups per CTA
   constexpr int H2 = NV / 2;                             // float2 pairs per lane
   extern __shared__ uint4 smem[];
   const int LP = a.L * a.P;

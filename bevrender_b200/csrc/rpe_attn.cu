@@ -438,8 +438,6 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
   const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
-  const float* kb = a.k + (size_t)bh * DH * a.Ns;
-  const float* vb = a.v + (size_t)bh * DH * a.Ns;
   const float2* pb = reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns;
 
   const int i0 = blockIdx.x * TQM + warp * 16;
@@ -717,8 +715,6 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
   const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
-  const float* kb = a.k + (size_t)bh * DH * a.Ns;
-  const float* vb = a.v + (size_t)bh * DH * a.Ns;
   const float2* pb = reinterpret_cast<const float2*>(a.pos) + (size_t)bg * a.Ns;
 
   const int i0 = blockIdx.x * TQM + warp * 16;
@@ -1008,8 +1004,6 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
   float* gtable = a.grad_rpe_pad ? a.grad_rpe_pad + ((size_t)((blockIdx.x + blockIdx.y) % a.gcopies) * a.h + head) * a.Hp * a.Wp +
                                        2 * a.Wp + 2 : nullptr;
-  const float* qb = a.q + (size_t)bh * DH * a.Nq;
-  const float* gb = a.grad_out + (size_t)bh * DH * a.Nq;
   const bool want_bias_grad = (a.grad_rpe_pad != nullptr) || (a.grad_pos != nullptr);
 
   const int j0w = blockIdx.x * TKM + warp * 16;
