@@ -24,7 +24,7 @@
 
 // tunables (overridable with -D for sweeps; defaults are the measured best, see profiles/r1_results.md)
 #ifndef MSDA_FWD_MINB
-#define MSDA_FWD_MINB 6
+#define MSDA_FWD_MINB 4
 #endif
 #ifndef MSDA_BWD_MINB
 #define MSDA_BWD_MINB 4
