@@ -637,22 +637,26 @@ def main():
                                                     qsplit=int(os.environ.get("BEVR_QSPLIT", "4")),
                                                     nslots=int(os.environ.get("BEVR_NSLOTS", "2")))
 
-    def e2e_step():
-        pipe.run(h_in, h_out)
+    # consecutive steps are enqueued back to back (join=False): step i+1's uploads start while step i's last results are
+    # still going down, as a loop that prefetches its next batch does; the pipeline is joined inside the timed region
+    def e2e_step(last=True):
+        pipe.run(h_in, h_out, join=last)
 
     e2e_steps = 0 if args.no_e2e else max(2, min(args.steps, 5))
     for _ in range(2 if e2e_steps else 0):
         e2e_step()
     barrier()
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    for i in range(e2e_steps):
+        e2e_step(last=(i == e2e_steps - 1) or bool(int(os.environ.get("BEVR_E2E_JOIN_EVERY_STEP", "0"))))
     e1.record()
     barrier()
     ms_e2e = max_over_ranks(e0.elapsed_time(e1)) / max(e2e_steps, 1)
     e2e = None if args.no_e2e else {"value": world * B * Nq / (ms_e2e * 1e-3), "unit": "queries/s", "ms_per_step": ms_e2e,
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "steps": e2e_steps,
-           "host_cpus_bound": None if cpus is None else len(cpus)}
+           "host_cpus_bound": None if cpus is None else len(cpus),
+           "pipelining": "per-sample / per-row-block pieces over H2D, compute and D2H streams; consecutive steps are enqueued "
+                         "back to back and joined inside the timed region (BEVR_E2E_JOIN_EVERY_STEP=1 joins after every step)"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

@@ -53,21 +53,37 @@ class HostMsdaPipeline:
         nws = _lib.lib().bevr_msda_bwd_workspace_bytes(c, self.S, h, Dh, self.dt)
         self.ws = [torch.empty(max(nws, 16), dtype=torch.uint8, device=self.dev) for _ in range(nslots)]
         self.s_in, self.s_cmp, self.s_out = (torch.cuda.Stream(self.dev) for _ in range(3))
+        self.ev_out = [None] * nslots          # per staging slot: its last download (also across calls of run)
+        self._forked = False
 
     def bytes_per_sample(self):
         n = lambda d: sum(t.numel() * t.element_size() for t in d.values()) // self.chunk
         return n(self.slots[0]["in"]), n(self.slots[0]["out"])
 
-    def run(self, h_in, h_out):
-        """h_in / h_out: dicts of PINNED host tensors with a leading batch dimension (B % chunk == 0)."""
+    def join(self):
+        """Make the caller's current stream wait for everything ``run(..., join=False)`` has enqueued."""
+        cur = torch.cuda.current_stream(self.dev)
+        for s in (self.s_in, self.s_cmp, self.s_out):
+            cur.wait_stream(s)
+        self._forked = False
+
+    def run(self, h_in, h_out, join=True):
+        """h_in / h_out: dicts of PINNED host tensors with a leading batch dimension (B % chunk == 0).
+
+        ``join=False`` returns without making the current stream wait for the pipeline: a following ``run`` then starts
+        uploading while this call's last results are still going down (the staging slots are handed over with events), as
+        a training loop that prefetches its next batch does.  Call ``join()`` (or ``run(join=True)``) before reading
+        ``h_out`` of the earlier calls from the current stream / after a synchronize."""
         L = _lib.lib()
         B = h_in["value"].shape[0]
         P = lambda t: C.c_void_p(t.data_ptr())
         cur = torch.cuda.current_stream(self.dev)
-        for s in (self.s_in, self.s_cmp, self.s_out):
-            s.wait_stream(cur)
+        if not self._forked:                                       # first call since the last join: order after the caller
+            for s in (self.s_in, self.s_cmp, self.s_out):
+                s.wait_stream(cur)
+            self._forked = True
         ns = self.nslots
-        ev_out = [None] * ns
+        ev_out = self.ev_out
         c = self.chunk
         split = len(self.qblocks) > 1 and c == 1
         blocks = self.qblocks if split else [(0, self.Nq)]
@@ -104,5 +120,5 @@ class HostMsdaPipeline:
                     if bi == len(blocks) - 1:
                         h_out["grad_value"][sl].copy_(o["grad_value"], non_blocking=True)
                         ev_out[i % ns] = self.s_out.record_event()
-        for s in (self.s_in, self.s_cmp, self.s_out):
-            cur.wait_stream(s)
+        if join:
+            self.join()
