@@ -366,8 +366,11 @@ constexpr int TQM = 64;                      // query rows per CTA (4 warps x 16
 #ifndef K3_MMA_CH
 #define K3_MMA_CH 32
 #endif
+#ifndef K3_FWD_Q_SMEM
+#define K3_FWD_Q_SMEM 0                      // forward: Q fragments in shared memory instead of 32 registers (5 CTAs per SM)
+#endif
 #ifndef K3_MMA_MINB
-#define K3_MMA_MINB 4
+#define K3_MMA_MINB (K3_FWD_Q_SMEM ? 5 : 4)
 #endif
 constexpr int CHM = K3_MMA_CH;               // keys per online-softmax step (4 n-tiles)
 
@@ -435,6 +438,10 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
   constexpr int NT = CHM / 8;                // key n-tiles per softmax step = k-steps of O += P V
   __shared__ __align__(16) float sKh[TK * PAD], sKl[TK * PAD], sVh[TK * PAD], sVl[TK * PAD];
   __shared__ __align__(16) float2 sPos[TK];
+#if K3_FWD_Q_SMEM
+  extern __shared__ __align__(16) float4 s_qf[];           // the warp's Q fragments (A operand of S), split when used
+  float4 (*sQf)[KS][32] = reinterpret_cast<float4 (*)[KS][32]>(s_qf);
+#endif
   const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
@@ -443,7 +450,9 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
   const int i0 = blockIdx.x * TQM + warp * 16;
   int iq[2] = {i0 + g, i0 + g + 8};
   float ay[2], ax[2], m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+#if !K3_FWD_Q_SMEM
   uint32_t qh[KS][4], ql[KS][4];
+#endif
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int iy = iq[r] / a.Wq, ixq = iq[r] - iy * a.Wq;
@@ -456,8 +465,12 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
     for (int e = 0; e < 4; ++e) {            // a0 (g, t)  a1 (g+8, t)  a2 (g, t+4)  a3 (g+8, t+4)
       const int r = e & 1, c = ks * 8 + t + ((e >> 1) << 2);
       const float x = iq[r] < a.Nq ? __ldg(a.q + ((size_t)bh * DH + c) * a.Nq + iq[r]) * a.scale : 0.f;
+#if K3_FWD_Q_SMEM
+      reinterpret_cast<float*>(&sQf[warp][ks][lane])[e] = x;
+#else
       qh[ks][e] = tf32_hi(x);
       ql[ks][e] = __float_as_uint(x - __uint_as_float(qh[ks][e]));
+#endif
     }
   float o[KS][4];
 #pragma unroll
@@ -498,12 +511,24 @@ __global__ void __launch_bounds__(128, K3_MMA_MINB) rpe_attn_fwd_mma_kernel(cons
           kl[nt][0] = __float_as_uint(sKl[off]); kl[nt][1] = __float_as_uint(sKl[off + 4]);
         }
         // the three products of one accumulator are issued NT tiles apart (they depend on each other)
+#if K3_FWD_Q_SMEM
+        uint32_t ah[4], al[4];
+        {
+          const float4 f = sQf[warp][ks][lane];
+          const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], qh[ks], kh[nt][0], kh[nt][1]);
+          for (int e = 0; e < 4; ++e) { ah[e] = tf32_hi(fv[e]); al[e] = __float_as_uint(fv[e] - __uint_as_float(ah[e])); }
+        }
+#else
+        const uint32_t (&ah)[4] = qh[ks];
+        const uint32_t (&al)[4] = ql[ks];
+#endif
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], qh[ks], kl[nt][0], kl[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ah, kh[nt][0], kh[nt][1]);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ql[ks], kh[nt][0], kh[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ah, kl[nt][0], kl[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], al, kh[nt][0], kh[nt][1]);
       }
       // ---- + sampled bias; element e of tile nt: row (e >> 1), key jc + nt*8 + 2t + (e & 1)
       float mx[2] = {-INFINITY, -INFINITY};
@@ -704,14 +729,23 @@ __global__ void __launch_bounds__(TQ, K3_DQ_MINB) rpe_attn_bwd_dq_kernel(const _
 #ifndef K3_DQ_MMA
 #define K3_DQ_MMA 1
 #endif
+#ifndef K3_DQ_QG_SMEM
+#define K3_DQ_QG_SMEM 0                      // dQ kernel: Q / dO fragments in shared memory instead of 64 registers (measured: slower here, 7.24 vs 7.05 ms SCA bwd)
+#endif
 #ifndef K3_DQ_MMA_MINB
-#define K3_DQ_MMA_MINB 3
+#define K3_DQ_MMA_MINB (K3_DQ_QG_SMEM ? 4 : 3)
 #endif
 template <int DH, bool DROP>
 __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kernel(const __grid_constant__ RpeArgs a) {
   constexpr int KS = DH / 8, NT = CHM / 8;
   __shared__ __align__(16) float sKh[TK * PAD], sKl[TK * PAD], sVh[TK * PAD], sVl[TK * PAD];
   __shared__ __align__(16) float2 sPos[TK];
+#if K3_DQ_QG_SMEM
+  // the warp's Q / dO fragments (A operands of S and dP) in shared memory, split into tf32 hi / lo when used (see the dK/dV kernel)
+  extern __shared__ __align__(16) float4 s_qgf[];
+  float4 (*sQf)[KS][32] = reinterpret_cast<float4 (*)[KS][32]>(s_qgf);
+  float4 (*sGf)[KS][32] = reinterpret_cast<float4 (*)[KS][32]>(s_qgf + 4 * KS * 32);
+#endif
   const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
@@ -720,7 +754,9 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
   const int i0 = blockIdx.x * TQM + warp * 16;
   const int iq[2] = {i0 + g, i0 + g + 8};
   float ay[2], ax[2], lse[2], delta[2];
+#if !K3_DQ_QG_SMEM
   uint32_t qh[KS][4], ql[KS][4], gh[KS][4], gl[KS][4];
+#endif
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int iy = iq[r] / a.Wq, ixq = iq[r] - iy * a.Wq;
@@ -738,8 +774,13 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
       const size_t idx = ((size_t)bh * DH + c) * a.Nq + iq[r];
       const float x = iq[r] < a.Nq ? __ldg(a.q + idx) * a.scale : 0.f;
       const float y = iq[r] < a.Nq ? __ldg(a.grad_out + idx) : 0.f;
+#if K3_DQ_QG_SMEM
+      reinterpret_cast<float*>(&sQf[warp][ks][lane])[e] = x;
+      reinterpret_cast<float*>(&sGf[warp][ks][lane])[e] = y;
+#else
       qh[ks][e] = tf32_hi(x); ql[ks][e] = __float_as_uint(x - __uint_as_float(qh[ks][e]));
       gh[ks][e] = tf32_hi(y); gl[ks][e] = __float_as_uint(y - __uint_as_float(gh[ks][e]));
+#endif
     }
   float dq[KS][4];
 #pragma unroll
@@ -780,24 +821,48 @@ __global__ void __launch_bounds__(128, K3_DQ_MMA_MINB) rpe_attn_bwd_dq_mma_kerne
           bh_[nt][0] = __float_as_uint(sKh[off]); bh_[nt][1] = __float_as_uint(sKh[off + 4]);
           bl_[nt][0] = __float_as_uint(sKl[off]); bl_[nt][1] = __float_as_uint(sKl[off + 4]);
         }
+#if K3_DQ_QG_SMEM
+        uint32_t ah[4], al[4];
+        {
+          const float4 f = sQf[warp][ks][lane];
+          const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], qh[ks], bh_[nt][0], bh_[nt][1]);
+          for (int e = 0; e < 4; ++e) { ah[e] = tf32_hi(fv[e]); al[e] = __float_as_uint(fv[e] - __uint_as_float(ah[e])); }
+        }
+#else
+        const uint32_t (&ah)[4] = qh[ks];
+        const uint32_t (&al)[4] = ql[ks];
+#endif
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], qh[ks], bl_[nt][0], bl_[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ah, bh_[nt][0], bh_[nt][1]);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ql[ks], bh_[nt][0], bh_[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ah, bl_[nt][0], bl_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], al, bh_[nt][0], bh_[nt][1]);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const int off = (jc + nt * 8 + g) * PAD + ks * 8 + t;
           bh_[nt][0] = __float_as_uint(sVh[off]); bh_[nt][1] = __float_as_uint(sVh[off + 4]);
           bl_[nt][0] = __float_as_uint(sVl[off]); bl_[nt][1] = __float_as_uint(sVl[off + 4]);
         }
+#if K3_DQ_QG_SMEM
+        uint32_t wh[4], wl[4];
+        {
+          const float4 f = sGf[warp][ks][lane];
+          const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], gh[ks], bh_[nt][0], bh_[nt][1]);
+          for (int e = 0; e < 4; ++e) { wh[e] = tf32_hi(fv[e]); wl[e] = __float_as_uint(fv[e] - __uint_as_float(wh[e])); }
+        }
+#else
+        const uint32_t (&wh)[4] = gh[ks];
+        const uint32_t (&wl)[4] = gl[ks];
+#endif
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], gh[ks], bl_[nt][0], bl_[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], wh, bh_[nt][0], bh_[nt][1]);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], gl[ks], bh_[nt][0], bh_[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], wh, bl_[nt][0], bl_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], wl, bh_[nt][0], bh_[nt][1]);
       }
       // dS = P (dP - delta), P = exp(S + bias - lse); element e of tile nt: row (e >> 1), key jc + nt*8 + 2t + (e & 1)
 #pragma unroll
@@ -989,8 +1054,11 @@ __global__ void __launch_bounds__(TKB * CS, DKV_MINB) rpe_attn_bwd_dkv_kernel(co
 #ifndef K3_DKV_MMA
 #define K3_DKV_MMA 1
 #endif
+#ifndef K3_DKV_KV_SMEM
+#define K3_DKV_KV_SMEM 1                     // dK/dV kernel: the resident K / V fragments in shared memory instead of 64 registers
+#endif
 #ifndef K3_DKV_MMA_MINB
-#define K3_DKV_MMA_MINB 3
+#define K3_DKV_MMA_MINB (K3_DKV_KV_SMEM ? 4 : 3)
 #endif
 constexpr int TKM = 64;                      // keys per CTA (4 warps x 16)
 
@@ -999,6 +1067,14 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
   constexpr int KS = DH / 8, NT = CHM / 8;
   __shared__ __align__(16) float sQh[TK * PAD], sQl[TK * PAD], sGh[TK * PAD], sGl[TK * PAD];
   __shared__ __align__(16) float4 sRow[TK];  // query halves of the bias coordinates (y, x), lse, delta
+#if K3_DKV_KV_SMEM
+  // the warp's K / V fragments (A operands of S^T and dP^T) live in shared memory, one float4 {a0, a1, a2, a3} per
+  // (k-step, lane), and are split into tf32 hi / lo when used: 64 registers less per thread (168 -> 4 CTAs per SM at 128)
+  // (dynamic: with the staged Q / dO tiles the kernel needs more than the 48 KB a kernel may declare statically)
+  extern __shared__ __align__(16) float4 s_kvf[];
+  float4 (*sKf)[KS][32] = reinterpret_cast<float4 (*)[KS][32]>(s_kvf);
+  float4 (*sVf)[KS][32] = reinterpret_cast<float4 (*)[KS][32]>(s_kvf + 4 * KS * 32);
+#endif
   const int bh = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   const int head = bh % a.h, bg = bh / a.hpg;
   const float* table = opaque_f(a.rpe_pad + (size_t)head * a.Hp * a.Wp + 2 * a.Wp + 2);
@@ -1009,7 +1085,9 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
   const int j0w = blockIdx.x * TKM + warp * 16;
   const int jk[2] = {j0w + g, j0w + g + 8};
   float by[2], bx[2], giy[2] = {0.f, 0.f}, gix[2] = {0.f, 0.f};
+#if !K3_DKV_KV_SMEM
   uint32_t kh[KS][4], kl[KS][4], vh[KS][4], vl[KS][4];
+#endif
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     float2 p = make_float2(0.f, 0.f);
@@ -1024,8 +1102,13 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
       const size_t idx = ((size_t)bh * DH + c) * a.Ns + jk[r];
       const float x = jk[r] < a.Ns ? __ldg(a.k + idx) : 0.f;
       const float y = jk[r] < a.Ns ? __ldg(a.v + idx) : 0.f;
+#if K3_DKV_KV_SMEM
+      reinterpret_cast<float*>(&sKf[warp][ks][lane])[e] = x;
+      reinterpret_cast<float*>(&sVf[warp][ks][lane])[e] = y;
+#else
       kh[ks][e] = tf32_hi(x); kl[ks][e] = __float_as_uint(x - __uint_as_float(kh[ks][e]));
       vh[ks][e] = tf32_hi(y); vl[ks][e] = __float_as_uint(y - __uint_as_float(vh[ks][e]));
+#endif
     }
   float dk[KS][4], dv[KS][4];
 #pragma unroll
@@ -1071,24 +1154,48 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
           bh_[nt][0] = __float_as_uint(sQh[off]); bh_[nt][1] = __float_as_uint(sQh[off + 4]);
           bl_[nt][0] = __float_as_uint(sQl[off]); bl_[nt][1] = __float_as_uint(sQl[off + 4]);
         }
+#if K3_DKV_KV_SMEM
+        uint32_t ah[4], al[4];
+        {
+          const float4 f = sKf[warp][ks][lane];
+          const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], kh[ks], bh_[nt][0], bh_[nt][1]);
+          for (int e = 0; e < 4; ++e) { ah[e] = tf32_hi(fv[e]); al[e] = __float_as_uint(fv[e] - __uint_as_float(ah[e])); }
+        }
+#else
+        const uint32_t (&ah)[4] = kh[ks];
+        const uint32_t (&al)[4] = kl[ks];
+#endif
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], kh[ks], bl_[nt][0], bl_[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ah, bh_[nt][0], bh_[nt][1]);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], kl[ks], bh_[nt][0], bh_[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], ah, bl_[nt][0], bl_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(sc[nt], al, bh_[nt][0], bh_[nt][1]);
 #pragma unroll
         for (int nt = 0; nt < NT; ++nt) {
           const int off = (jc + nt * 8 + g) * PAD + ks * 8 + t;
           bh_[nt][0] = __float_as_uint(sGh[off]); bh_[nt][1] = __float_as_uint(sGh[off + 4]);
           bl_[nt][0] = __float_as_uint(sGl[off]); bl_[nt][1] = __float_as_uint(sGl[off + 4]);
         }
+#if K3_DKV_KV_SMEM
+        uint32_t wh[4], wl[4];
+        {
+          const float4 f = sVf[warp][ks][lane];
+          const float fv[4] = {f.x, f.y, f.z, f.w};
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], vh[ks], bh_[nt][0], bh_[nt][1]);
+          for (int e = 0; e < 4; ++e) { wh[e] = tf32_hi(fv[e]); wl[e] = __float_as_uint(fv[e] - __uint_as_float(wh[e])); }
+        }
+#else
+        const uint32_t (&wh)[4] = vh[ks];
+        const uint32_t (&wl)[4] = vl[ks];
+#endif
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], vh[ks], bl_[nt][0], bl_[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], wh, bh_[nt][0], bh_[nt][1]);
 #pragma unroll
-        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], vl[ks], bh_[nt][0], bh_[nt][1]);
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], wh, bl_[nt][0], bl_[nt][1]);
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt) mma_tf32(dp[nt], wl, bh_[nt][0], bh_[nt][1]);
       }
       // P^T -> sc, dS^T -> dp (in place), bias gradients
 #pragma unroll
@@ -1325,7 +1432,22 @@ static int rpe_fwd_impl(const float* q, const float* k, const float* v, const fl
   }
   if (mma) {
     dim3 grid((a.Nq + TQM - 1) / TQM, BH, a.split);
+#if K3_FWD_Q_SMEM
+    {
+      const size_t dyn = 4 * (size_t)(Dh / 8) * 32 * sizeof(float4);
+      auto launch_fwd = [&](auto kern) {
+        if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "rpe_attn_fwd shared memory")) return rc;
+        kern<<<grid, 128, dyn, st>>>(a);
+        return 0;
+      };
+      int rc;
+      if (Dh == 32) rc = a.drop_thresh ? launch_fwd(rpe_attn_fwd_mma_kernel<32, true>) : launch_fwd(rpe_attn_fwd_mma_kernel<32, false>);
+      else rc = a.drop_thresh ? launch_fwd(rpe_attn_fwd_mma_kernel<16, true>) : launch_fwd(rpe_attn_fwd_mma_kernel<16, false>);
+      if (rc) return rc;
+    }
+#else
     K3_LAUNCH(rpe_attn_fwd_mma_kernel, grid, 128);
+#endif
   } else {
     dim3 grid((a.Nq + TQ - 1) / TQ, BH, a.split);
     K3_LAUNCH(rpe_attn_fwd_kernel, grid, TQ / RQ);
@@ -1401,7 +1523,22 @@ static int rpe_bwd_impl(const float* q, const float* k, const float* v, const fl
     a.split = pick_split((long long)nqt * BH, mma_dq ? K3_DQ_MMA_MINB : K3_DQ_MINB, (Ns + TK - 1) / TK, &a.tiles_per_split);
     if (a.split > 1)
       if (int rc = check_cuda(cudaMemsetAsync(grad_q, 0, (size_t)BH * Dh * a.Nq * sizeof(float), st), "rpe_attn_bwd zero-fill")) return rc;
-    if (mma_dq) K3_LAUNCH(rpe_attn_bwd_dq_mma_kernel, dim3(nqt, BH, a.split), 128);
+    if (mma_dq) {
+#if K3_DQ_QG_SMEM
+      const size_t dyn = 2 * 4 * (size_t)(Dh / 8) * 32 * sizeof(float4);      // Q and dO fragments of the CTA's 4 warps
+      auto launch_dq = [&](auto kern) {
+        if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "rpe_attn_bwd dq shared memory")) return rc;
+        kern<<<dim3(nqt, BH, a.split), 128, dyn, st>>>(a);
+        return 0;
+      };
+      int rc;
+      if (Dh == 32) rc = a.drop_thresh ? launch_dq(rpe_attn_bwd_dq_mma_kernel<32, true>) : launch_dq(rpe_attn_bwd_dq_mma_kernel<32, false>);
+      else rc = a.drop_thresh ? launch_dq(rpe_attn_bwd_dq_mma_kernel<16, true>) : launch_dq(rpe_attn_bwd_dq_mma_kernel<16, false>);
+      if (rc) return rc;
+#else
+      K3_LAUNCH(rpe_attn_bwd_dq_mma_kernel, dim3(nqt, BH, a.split), 128);
+#endif
+    }
     else K3_LAUNCH(rpe_attn_bwd_dq_kernel, dim3(nqt, BH, a.split), TQ);
     if (int rc = check_launch("rpe_attn_bwd dq")) return rc;
   }
@@ -1416,7 +1553,22 @@ static int rpe_bwd_impl(const float* q, const float* k, const float* v, const fl
       if (grad_v)
         if (int rc = check_cuda(cudaMemsetAsync(grad_v, 0, (size_t)BH * Dh * Ns * sizeof(float), st), "rpe_attn_bwd zero-fill")) return rc;
     }
-    if (mma_dkv) K3_LAUNCH(rpe_attn_bwd_dkv_mma_kernel, dim3(nkt, BH, a.split), 128);
+    if (mma_dkv) {
+#if K3_DKV_KV_SMEM
+      const size_t dyn = 2 * 4 * (size_t)(Dh / 8) * 32 * sizeof(float4);      // K and V fragments of the CTA's 4 warps
+      auto launch_dkv = [&](auto kern) {
+        if (int rc = check_cuda(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn), "rpe_attn_bwd dkv shared memory")) return rc;
+        kern<<<dim3(nkt, BH, a.split), 128, dyn, st>>>(a);
+        return 0;
+      };
+      int rc;
+      if (Dh == 32) rc = a.drop_thresh ? launch_dkv(rpe_attn_bwd_dkv_mma_kernel<32, true>) : launch_dkv(rpe_attn_bwd_dkv_mma_kernel<32, false>);
+      else rc = a.drop_thresh ? launch_dkv(rpe_attn_bwd_dkv_mma_kernel<16, true>) : launch_dkv(rpe_attn_bwd_dkv_mma_kernel<16, false>);
+      if (rc) return rc;
+#else
+      K3_LAUNCH(rpe_attn_bwd_dkv_mma_kernel, dim3(nkt, BH, a.split), 128);
+#endif
+    }
     else K3_LAUNCH(rpe_attn_bwd_dkv_kernel, dim3(nkt, BH, a.split), TKB * CS);
     if (int rc = check_launch("rpe_attn_bwd dkv")) return rc;
   }
