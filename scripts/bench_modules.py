@@ -26,6 +26,7 @@ def timeit(fn, warm=3, iters=10):
 
 def main():
     env = lambda k, d: int(os.environ.get(k, d))
+    bb.SCADeformableAttention.sort_keys = bool(env("SORT_KEYS", 1))
     B, N, C, h, D = env("B", 8), env("N", 56), env("C", 64), env("H", 2), env("D", 5)
     iters = env("ITERS", 10)
     torch.manual_seed(0)
