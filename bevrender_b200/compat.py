@@ -66,7 +66,8 @@ def ensure_timm_stub():
 
 def install(projector=True, wrappers=False):
     """``wrappers=True`` additionally rebinds ``model.encoder.{SpatialCrossAttn, TemporalSelfAttn}`` to the versions
-    that cache the projected reference points on the device (no per-forward upload / ``.item()`` sync)."""
+    that cache the projected reference points on the device (no per-forward upload / ``.item()`` sync) and routes
+    ``EncoderLayer.project_history_bev_feat`` to the batched history-BEV warp kernel (row f-1)."""
     from . import BEV2CameraProjector, SCADeformableAttention, TSADeformableAttention
     ensure_timm_stub()
     tsa = importlib.import_module("model.TSA")
@@ -74,9 +75,23 @@ def install(projector=True, wrappers=False):
     tsa.TSADeformableAttention = TSADeformableAttention
     sca.SCADeformableAttention = SCADeformableAttention
     if wrappers:
-        from . import SpatialCrossAttn, TemporalSelfAttn
+        from . import SpatialCrossAttn, TemporalSelfAttn, project_history_bev
         enc = importlib.import_module("model.encoder")
         enc.SpatialCrossAttn, enc.TemporalSelfAttn = SpatialCrossAttn, TemporalSelfAttn
+        # row f-1: EncoderLayer.project_history_bev_feat (encoder.py:413-466) loops over the samples with two torchvision
+        # F.affine calls each and math.degrees(tensor) / tuple(tensor) host syncs (~4 syncs and ~20 tiny kernels per sample,
+        # per layer, per history frame).  The batched warp kernel serves the case the model actually runs -- history
+        # features carry no gradient (bevrender.py:124-146 computes them under no_grad) and no mask is asked for; every
+        # other case goes to the reference's own method.
+        if not hasattr(enc.EncoderLayer, "_bevr_reference_project_history"):
+            enc.EncoderLayer._bevr_reference_project_history = enc.EncoderLayer.project_history_bev_feat
+
+            def project_history_bev_feat(self, bev, vehicle_pose, return_mask=False):
+                if return_mask or not bev.is_cuda or bev.requires_grad or bev.dim() != 4:
+                    return self._bevr_reference_project_history(bev, vehicle_pose, return_mask)
+                return project_history_bev(bev, vehicle_pose)
+
+            enc.EncoderLayer.project_history_bev_feat = project_history_bev_feat
     if projector:
         try:
             top = importlib.import_module("model.bevrender")
