@@ -1062,7 +1062,7 @@ __global__ void __launch_bounds__(TKB * CS, DKV_MINB) rpe_attn_bwd_dkv_kernel(co
 #endif
 constexpr int TKM = 64;                      // keys per CTA (4 warps x 16)
 
-template <int DH, bool DROP>
+template <int DH, bool DROP, bool MERGE>
 __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_kernel(const __grid_constant__ RpeArgs a) {
   constexpr int KS = DH / 8, NT = CHM / 8;
   __shared__ __align__(16) float sQh[TK * PAD], sQl[TK * PAD], sGh[TK * PAD], sGl[TK * PAD];
@@ -1222,10 +1222,31 @@ __global__ void __launch_bounds__(128, K3_DKV_MMA_MINB) rpe_attn_bwd_dkv_mma_ker
               float* g1 = g0 + a.Wp;
               const float dx0 = ds * b.wx0, dx1 = ds * b.wx1;
               float l0 = dx0 * b.wy0, l1 = dx0 * b.wy1;            // taps (y0, x0), (y0+1, x0)
-              const float r0 = dx1 * b.wy0, r1 = dx1 * b.wy1;      // taps (y0, x0+1), (y0+1, x0+1)
+              float r0 = dx1 * b.wy0, r1 = dx1 * b.wy1;            // taps (y0, x0+1), (y0+1, x0+1)
               // Neighbouring key rows of the tile (lanes 4 apart) sit one table cell apart, so the right-hand taps of
               // key g+1 are the left-hand taps of key g: hand them over with shuffles and halve the RED sectors.
               const int off_up = __shfl_down_sync(0xffffffffu, b.off, 4), off_dn = __shfl_up_sync(0xffffffffu, b.off, 4);
+              // Key rows that address the SAME cell (SCA's masked reference points, once the module has ordered the keys
+              // by table row and x: ~60 keys per cell) are not coalesced by the memory system -- every lane of a RED
+              // instruction with an equal address is its own L2 reduction.  When any two neighbouring key rows of the warp
+              // agree (warp-uniform test, free: off_up is needed anyway), the runs of equal cells of each query column are
+              // summed with a segmented suffix scan over the 8 key rows and only the run heads issue atomics.
+              // MERGE is a per-call flag (BEVR_K3_RUN_MERGE): the instantiation without it is the plain kernel.
+              if (MERGE && __any_sync(0xffffffffu, g < 7 && off_up == b.off)) {
+                const bool head = g == 0 || off_dn != b.off;
+                const unsigned hx = (__ballot_sync(0xffffffffu, head) >> t) & 0x11111111u;   // heads of this column, bit 4 g'
+#pragma unroll
+                for (int d = 1; d < 8; d <<= 1) {
+                  const float p0 = __shfl_down_sync(0xffffffffu, l0, 4 * d), p1 = __shfl_down_sync(0xffffffffu, l1, 4 * d);
+                  const float p2 = __shfl_down_sync(0xffffffffu, r0, 4 * d), p3 = __shfl_down_sync(0xffffffffu, r1, 4 * d);
+                  // rows g+1 .. g+d hold no run head <=> row g+d continues the run of row g
+                  const unsigned span = (g + 1 < 8 ? (0x11111111u << (4 * (g + 1))) : 0u) &
+                                        ~(g + d + 1 < 8 ? (0x11111111u << (4 * (g + d + 1))) : 0u);
+                  if (g + d < 8 && !(hx & span)) { l0 += p0; l1 += p1; r0 += p2; r1 += p3; }
+                }
+                if (head) { atomicAdd(g0, l0); atomicAdd(g1, l1); atomicAdd(g0 + 1, r0); atomicAdd(g1 + 1, r1); }
+                continue;
+              }
               const float in0 = __shfl_down_sync(0xffffffffu, r0, 4), in1 = __shfl_down_sync(0xffffffffu, r1, 4);
               if (g < 7 && off_up + 1 == b.off) { l0 += in0; l1 += in1; }
               atomicAdd(g0, l0); atomicAdd(g1, l1);
@@ -1562,11 +1583,18 @@ static int rpe_bwd_impl(const float* q, const float* k, const float* v, const fl
         return 0;
       };
       int rc;
-      if (Dh == 32) rc = a.drop_thresh ? launch_dkv(rpe_attn_bwd_dkv_mma_kernel<32, true>) : launch_dkv(rpe_attn_bwd_dkv_mma_kernel<32, false>);
-      else rc = a.drop_thresh ? launch_dkv(rpe_attn_bwd_dkv_mma_kernel<16, true>) : launch_dkv(rpe_attn_bwd_dkv_mma_kernel<16, false>);
+      const bool mg = (flags & BEVR_K3_RUN_MERGE) != 0;
+      if (Dh == 32) {
+        if (mg) rc = a.drop_thresh ? launch_dkv(rpe_attn_bwd_dkv_mma_kernel<32, true, true>) : launch_dkv(rpe_attn_bwd_dkv_mma_kernel<32, false, true>);
+        else rc = a.drop_thresh ? launch_dkv(rpe_attn_bwd_dkv_mma_kernel<32, true, false>) : launch_dkv(rpe_attn_bwd_dkv_mma_kernel<32, false, false>);
+      } else {
+        if (mg) rc = a.drop_thresh ? launch_dkv(rpe_attn_bwd_dkv_mma_kernel<16, true, true>) : launch_dkv(rpe_attn_bwd_dkv_mma_kernel<16, false, true>);
+        else rc = a.drop_thresh ? launch_dkv(rpe_attn_bwd_dkv_mma_kernel<16, true, false>) : launch_dkv(rpe_attn_bwd_dkv_mma_kernel<16, false, false>);
+      }
       if (rc) return rc;
 #else
-      K3_LAUNCH(rpe_attn_bwd_dkv_mma_kernel, dim3(nkt, BH, a.split), 128);
+      if (Dh == 32) { if (a.drop_thresh) rpe_attn_bwd_dkv_mma_kernel<32, true, true><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a); else rpe_attn_bwd_dkv_mma_kernel<32, false, true><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a); }
+      else { if (a.drop_thresh) rpe_attn_bwd_dkv_mma_kernel<16, true, true><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a); else rpe_attn_bwd_dkv_mma_kernel<16, false, true><<<dim3(nkt, BH, a.split), 128, 0, st>>>(a); }
 #endif
     }
     else K3_LAUNCH(rpe_attn_bwd_dkv_kernel, dim3(nkt, BH, a.split), TKB * CS);

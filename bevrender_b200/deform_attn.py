@@ -113,7 +113,8 @@ class _DeformAttnBase(nn.Module):
         """gather (K1/K2) -> K/V projections -> fused RPE attention (K3) -> (B, C, Hq, Wq)."""
         B, C, Hq, Wq = query.shape
         Ns = pos.shape[1] * pos.shape[2]
-        if sort_keys and self.n_groups == 1:
+        sort_keys = sort_keys and self.n_groups == 1
+        if sort_keys:
             # Attention is invariant under a permutation of the keys (with several groups the K / V projections mix the
             # groups' channels at equal key index, so a per-group order is only available for n_groups == 1).  SCA's masked reference points all sit at (-1, -1)
             # plus their learned offsets (bev_cmr_proj.py:106-124): in the reference's key order eight consecutive keys
@@ -136,7 +137,7 @@ class _DeformAttnBase(nn.Module):
         # attention dropout (attn_drop_rate, TSA_deform_attn.py:313-323 / SCA_deform_attn.py:402-410) is fused into K3
         drop = float(self.attn_drop_rate.p) if self.training else 0.0
         out = rpe_attention(q, k, v, self.rpe_table, pos.reshape(-1, Ns, 2), Hq, Wq, self.n_groups, self.scale,
-                            dropout_p=drop)
+                            dropout_p=drop, merge_runs=sort_keys)
         return out.reshape(B, C, Hq, Wq)
 
 

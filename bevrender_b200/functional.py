@@ -185,7 +185,11 @@ class _RpeAttention(torch.autograd.Function):
 K3_AUTO, K3_FFMA, K3_MMA = 0, 1, 2
 
 
-def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None, family=K3_AUTO, dropout_p=0.0, seed=None):
+K3_RUN_MERGE = 4
+
+
+def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None, family=K3_AUTO, dropout_p=0.0, seed=None,
+                  merge_runs=False):
     """K3: softmax_j(q.k*scale + bilinear(rpe_table[head], (qgrid_i - pos_j)/2)) . v, never materialised.
 
     q (B*h, Dh, Hq*Wq); k, v (B*h, Dh, Ns); rpe_table (h, Rh, Rw); pos (B*g, Ns, 2) in (y, x);
@@ -194,6 +198,8 @@ def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None, famil
     ``dropout_p`` > 0: attention dropout fused into the kernels (nn.Dropout on the softmax matrix,
     TSA_deform_attn.py:313-323); the keep mask is a hash of (``seed``, head, query, key) regenerated in backward.
     ``seed`` None draws one from torch's default generator (so ``torch.manual_seed`` makes a run reproducible).
+    ``merge_runs``: the keys arrive ordered so that keys addressing the same table cell are consecutive
+    (BEVR_K3_RUN_MERGE): the backward sums such runs before the table-gradient atomics.
     """
     h = rpe_table.shape[0]
     if scale is None:
@@ -203,8 +209,8 @@ def rpe_attention(q, k, v, rpe_table, pos, Hq, Wq, n_groups=1, scale=None, famil
         raise ValueError(f"rpe_attention: dropout_p must be in [0, 1), got {dropout_p}")
     if dropout_p > 0.0 and seed is None:
         seed = int(torch.randint(0, 2 ** 62, (1,), dtype=torch.int64).item())
-    return _RpeAttention.apply(q, k, v, rpe_table, pos, int(Hq), int(Wq), h // n_groups, scale, int(family),
-                               dropout_p, int(seed or 0))
+    return _RpeAttention.apply(q, k, v, rpe_table, pos, int(Hq), int(Wq), h // n_groups, scale,
+                               int(family) | (K3_RUN_MERGE if merge_runs else 0), dropout_p, int(seed or 0))
 
 
 class _OffsetHead(torch.autograd.Function):

@@ -130,7 +130,10 @@ int bevr_project_points(const float* points, const float* cam_T, const float* K,
  * Requires Dh == 32 (the reference uses 32 channels per head everywhere, encoder.py:23-39) or Dh == 16.
  */
 size_t bevr_rpe_attn_workspace_bytes(int BH, int h, int Dh, int Nq, int Ns, int Rh, int Rw, int backward);
-enum { BEVR_K3_FFMA = 1, BEVR_K3_MMA = 2 };
+enum { BEVR_K3_FFMA = 1, BEVR_K3_MMA = 2,
+       BEVR_K3_RUN_MERGE = 4   /* backward (mma family): keys whose bias-table cells coincide arrive in runs (the caller
+                                  ordered them by table row and x, as the SCA module does for masked reference points):
+                                  the table-gradient scatter sums each run in the warp and issues one reduction per run */ };
 /* (the workspace size covers both families: it does not depend on `flags`) */
 int bevr_rpe_attn_fwd(const float* q, const float* k, const float* v, const float* rpe,
                       const float* pos, float* out, float* lse, void* workspace, int BH, int h,

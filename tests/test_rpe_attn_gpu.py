@@ -178,3 +178,33 @@ def test_module_attention_dropout_train_vs_eval():
     assert torch.equal(a, b) and not torch.equal(a, c)
     a.sum().backward()
     assert torch.isfinite(q.grad).all()
+
+
+@pytest.mark.parametrize("sort", [False, True], ids=["any-order", "sorted"])
+def test_run_merge_of_coincident_keys_is_exact(sort):
+    """BEVR_K3_RUN_MERGE (backward, mma family): keys that address the same bias-table cell -- SCA's masked reference
+    points at (-1, -1) plus small offsets -- are summed in the warp before the table-gradient atomics.  The merge must be
+    exact for ANY key order (it only merges neighbouring key rows with equal cells); ordered keys are the case it serves."""
+    import bevrender_b200 as bb
+    if FAMILY != 2:
+        pytest.skip("the run merge lives in the mma.sync dK/dV kernel")
+    B, h, g, Hq, Wq, Hk, Wk, mul = 1, 2, 1, 28, 28, 14, 140, 5
+    q, k, v, rpe, pos, go = _case(B, h, g, Hq, Wq, Hk, Wk, mul, 7, 0.05)
+    Ns = Hk * Wk
+    masked = torch.rand(B * g, Ns) < 0.4                                   # scattered through the key list
+    pos = torch.where(masked[..., None], -1.0 + 0.004 * torch.randn(B * g, Ns, 2), pos)
+    if sort:
+        Rh, Rw = rpe.shape[1:]
+        key = torch.floor((1.0 - pos[..., 0]) * (0.25 * (Rh - 1))) * 8192.0 - pos[..., 1] * (0.25 * (Rw - 1))
+        perm = torch.argsort(key, dim=1)
+        pos = torch.gather(pos, 1, perm[..., None].expand(-1, -1, 2))
+    cpu = [t.clone().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    ref = oda.rpe_attention_dense(*cpu, Hq, Wq, g, 32 ** -0.5)
+    ref.backward(go)
+    dev = [t.cuda().requires_grad_(True) for t in (q, k, v, rpe, pos)]
+    out = bb.rpe_attention(*dev, Hq, Wq, g, family=FAMILY, merge_runs=True)
+    out.backward(go.cuda())
+    assert rel_err(out.cpu(), ref) < FP32_TOL
+    for name, a, b in zip(("q", "k", "v", "rpe", "pos"), dev, cpu):
+        e = rel_err(a.grad.cpu(), b.grad)
+        assert e < FP32_TOL, f"grad_{name}: {e:.3e}"
