@@ -216,6 +216,36 @@ def test_host_pipeline_matches_device_path():
     assert rel_err(h_out["grad_weight"], gw.cpu()) < 1e-5
 
 
+def test_host_pipeline_back_to_back_calls_without_join():
+    """run(join=False) x3 + join(): consecutive calls overlap (the next call uploads while the previous one's last results go
+    down; staging slots are handed over with events) and every call's results are complete after the join -- different
+    inputs and output buffers per call, compared with joined runs of the same inputs."""
+    from bevrender_b200.host_pipeline import HostMsdaPipeline
+    ds = [make_microbench_inputs(3, seed=s, n_side=20, h=4, Dh=32, L=2, P=4) for s in (1, 2, 3)]
+    S = sum(h * w for h, w in ds[0]["spatial_shapes"])
+    pipe = HostMsdaPipeline(ds[0]["spatial_shapes"], ds[0]["level_start_index"], 4, 32, 400, 4, 20)
+    names = ("value", "sampling_locations", "attention_weights", "grad_out")
+    mk_out = lambda: {"out": torch.zeros(3, 400, 128).pin_memory(), "grad_value": torch.zeros(3, S, 4, 32).pin_memory(),
+                      "grad_loc": torch.zeros(3, 400, 4, 2, 4, 2).pin_memory(),
+                      "grad_weight": torch.zeros(3, 400, 4, 2, 4).pin_memory()}
+    h_ins = [{k: d[k].contiguous().pin_memory() for k in names} for d in ds]
+    want = []
+    for h_in in h_ins:
+        o = mk_out()
+        pipe.run(h_in, o)
+        torch.cuda.synchronize()
+        want.append(o)
+    got = [mk_out() for _ in ds]
+    for h_in, o in zip(h_ins, got):
+        pipe.run(h_in, o, join=False)
+    pipe.join()
+    torch.cuda.synchronize()
+    for w, g in zip(want, got):
+        assert torch.equal(g["out"], w["out"])
+        assert torch.equal(g["grad_loc"], w["grad_loc"]) and torch.equal(g["grad_weight"], w["grad_weight"])
+        assert rel_err(g["grad_value"], w["grad_value"]) < 1e-6          # atomics: order-dependent rounding only
+
+
 def test_empty_query_list():
     """Nq = 0: forward returns an empty tensor, backward a zero grad_value (no kernel launch)."""
     import bevrender_b200 as bb
