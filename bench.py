@@ -530,7 +530,7 @@ def main():
     warm = max(args.warmup, 3)
 
     # ---- synthetic inputs (pinned host copies for the e2e leg, device copies for the kernel leg)
-    host = make_microbench_inputs(B, seed=rank, dtype=tdt)
+    host = make_microbench_inputs(B, seed=rank, dtype=tdt, sigma_px=float(os.environ.get("BEVR_SIGMA_PX", "2.0")))
     shapes, starts = host["spatial_shapes"], host["level_start_index"]
     S = sum(h * w for h, w in shapes)
     Nq = N_SIDE * N_SIDE
