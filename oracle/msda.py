@@ -9,8 +9,11 @@ The general (L levels, P points, learned weights) form named by the north
 star has NO counterpart in the reference: for L>1 or P>1
 this oracle is the same construction the reference uses -- one
 ``F.grid_sample(bilinear, zeros)`` per level, weighted sum over points and
-levels -- and its parity is "unpinned vs reference" (pinned only against the
-numpy restatement in ``oracle/bilinear.py``).
+levels -- and its parity is "unpinned vs reference".  It IS pinned against two
+independent definitions: the numpy restatement of grid_sample in
+``oracle/bilinear.py`` and the published pure-PyTorch definition of the operator
+the north star names, Deformable DETR's ``ms_deform_attn_core_pytorch``
+(restated in ``oracle/msda_ddetr.py``; tests/test_oracle.py).
 
 Layouts (channels-last, the B200 kernels' native layout):
   value              (B, S, h, Dh)      S = sum_l H_l*W_l

@@ -130,3 +130,32 @@ def test_dropout_keep_mask_is_a_fair_coin_per_head_and_seed():
     assert torch.equal(a, oda.dropout_keep(7, 4, 50, 60, 0.25))
     assert not torch.equal(a[0], a[1]) and not torch.equal(a, oda.dropout_keep(8, 4, 50, 60, 0.25))
     assert oda.dropout_keep(7, 1, 8, 8, 0.0).all()
+
+
+@pytest.mark.parametrize("B,h,Dh,L,P,n", [(2, 4, 8, 3, 2, 12), (1, 8, 32, 4, 4, 10), (1, 2, 16, 1, 1, 9)])
+def test_msda_oracle_matches_deformable_detr_definition(B, h, Dh, L, P, n):
+    """oracle/msda.py (the checker of K1/K2) against the published pure-PyTorch definition of the operator it names
+    (Deformable DETR's ms_deform_attn_core_pytorch, restated in oracle/msda_ddetr.py): output and all three gradients,
+    locations partly outside [0, 1] (zero padding)."""
+    from oracle import msda as om
+    from oracle import msda_ddetr as dd
+    g = torch.Generator().manual_seed(5)
+    shapes = [(max(n >> l, 2), max((n + 3) >> l, 2)) for l in range(L)]
+    starts, s = [], 0
+    for H, W in shapes:
+        starts.append(s)
+        s += H * W
+    Nq = 37
+    value = torch.randn(B, s, h, Dh, generator=g, dtype=torch.float64)
+    loc = torch.rand(B, Nq, h, L, P, 2, generator=g, dtype=torch.float64) * 1.3 - 0.15
+    w = torch.softmax(torch.randn(B, Nq, h, L * P, generator=g, dtype=torch.float64), -1).reshape(B, Nq, h, L, P)
+    go = torch.randn(B, Nq, h * Dh, generator=g, dtype=torch.float64)
+    a = [t.clone().requires_grad_(True) for t in (value, loc, w)]
+    b = [t.clone().requires_grad_(True) for t in (value, loc, w)]
+    out_a = om.msda_forward(a[0], shapes, starts, a[1], a[2])
+    out_b = dd.ms_deform_attn_core(b[0], shapes, b[1], b[2])
+    out_a.backward(go)
+    out_b.backward(go)
+    assert torch.allclose(out_a, out_b, rtol=1e-12, atol=1e-12)
+    for x, y in zip(a, b):
+        assert torch.allclose(x.grad, y.grad, rtol=1e-10, atol=1e-12)
