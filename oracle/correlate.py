@@ -4,6 +4,8 @@ PARITY UNPINNED: the reference contains no registration / correlation code at al
 closest thing is a retrieval recall from ``2 - 2*X@Y.T`` in numpy, train.py:551-572), so this file DEFINES the
 operator the CUDA kernel implements: rotate the template about its centre with bilinear ``F.grid_sample``
 (zeros outside), then valid-mode cross-correlate every rotation with the map tile using ``F.conv2d``.
+The torch formulation is checked against plain numpy loops written from the formula in include/bevr.h
+(tests/test_oracle.py::test_correlation_oracle_matches_first_principles_loops).
 """
 import math
 

@@ -159,3 +159,40 @@ def test_msda_oracle_matches_deformable_detr_definition(B, h, Dh, L, P, n):
     assert torch.allclose(out_a, out_b, rtol=1e-12, atol=1e-12)
     for x, y in zip(a, b):
         assert torch.allclose(x.grad, y.grad, rtol=1e-10, atol=1e-12)
+
+
+def test_correlation_oracle_matches_first_principles_loops():
+    """oracle/correlate.py DEFINES K5's operator (the reference has no registration code): check the torch formulation
+    (grid_sample rotation + conv2d) against plain numpy loops written from the formula in include/bevr.h,
+      out[r, y, x] = sum_{c,u,v} map[c, y+u, x+v] * rot_r(tmpl)[c, u, v],
+      rot_r samples tmpl bilinearly (zeros outside) at centre + R(angle_r) (v - cx, u - cy)."""
+    import math
+    import numpy as np
+    from oracle import correlate as oc
+    rng = np.random.default_rng(3)
+    C_, Hm, Wm, Ht, Wt = 2, 9, 11, 4, 6
+    m = rng.standard_normal((C_, Hm, Wm))
+    t = rng.standard_normal((C_, Ht, Wt))
+    angles = [0.0, 0.4, -1.1, math.pi / 2]
+    cx, cy = 0.5 * (Wt - 1), 0.5 * (Ht - 1)
+
+    def tap(c, yy, xx):
+        return t[c, yy, xx] if 0 <= yy < Ht and 0 <= xx < Wt else 0.0
+
+    want = np.zeros((len(angles), Hm - Ht + 1, Wm - Wt + 1))
+    for r, a in enumerate(angles):
+        rot = np.zeros_like(t)
+        for u in range(Ht):
+            for v in range(Wt):
+                sx = cx + math.cos(a) * (v - cx) - math.sin(a) * (u - cy)
+                sy = cy + math.sin(a) * (v - cx) + math.cos(a) * (u - cy)
+                x0, y0 = math.floor(sx), math.floor(sy)
+                fx, fy = sx - x0, sy - y0
+                for c in range(C_):
+                    rot[c, u, v] = ((1 - fy) * ((1 - fx) * tap(c, y0, x0) + fx * tap(c, y0, x0 + 1)) +
+                                    fy * ((1 - fx) * tap(c, y0 + 1, x0) + fx * tap(c, y0 + 1, x0 + 1)))
+        for y in range(want.shape[1]):
+            for x in range(want.shape[2]):
+                want[r, y, x] = np.sum(m[:, y:y + Ht, x:x + Wt] * rot)
+    got = oc.correlate(torch.from_numpy(m), torch.from_numpy(t), angles).numpy()
+    assert np.allclose(got, want, rtol=1e-10, atol=1e-10)
